@@ -1,0 +1,485 @@
+// hgrid.cu -- solver handle, PCG driver and the C ABI of libhgrid.so (see include/hgrid.h).
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "pcg.cuh"
+#include "stencil.cuh"
+
+namespace hg {
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char buf_[512];                                                                        \
+            snprintf(buf_, sizeof buf_, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return fail(e_ == cudaErrorMemoryAllocation ? HG_ERR_NOMEM : HG_ERR_CUDA, buf_);        \
+        }                                                                                          \
+    } while (0)
+
+#define HGTRY(call)                 \
+    do {                            \
+        int rc_ = (call);           \
+        if (rc_ != HG_OK) return rc_; \
+    } while (0)
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+struct SolverBase {
+    virtual ~SolverBase() {}
+    virtual int set_flags(const uint8_t* f) = 0;
+    virtual int set_soft(const double* w, double scalar) = 0;
+    virtual int set_grad_weight(double w) = 0;
+    virtual int set_precond(int p) = 0;
+    virtual int setup(hg_setup_info* info) = 0;
+    virtual int apply(const double* x, double* y) = 0;
+    virtual int upload(const hg_values* v, hg_stats* st) = 0;
+    virtual int solve_device(double rtol, int maxiter, hg_stats* st) = 0;
+    virtual int download(double* x, hg_stats* st) = 0;
+    virtual int bench_apply(int iters, double* ms) = 0;
+};
+
+template <typename T>
+struct Solver : SolverBase {
+    int rows, cols, K, op, pitch;
+    long long plane;
+    int precond = HG_PRECOND_JACOBI;
+    bool flags_set = false, is_setup = false, have_values = false;
+    double soft_scalar = 0.0, w_g = 0.0;
+    bool soft_plane_set = false;
+
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    uint8_t* d_flags = nullptr;
+    T* d_soft = nullptr;
+    T* d_dinv = nullptr;
+    T *d_x = nullptr, *d_b = nullptr, *d_r = nullptr, *d_p = nullptr, *d_q = nullptr;
+    double* d_stage[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // staged host arrays
+    double* d_out = nullptr;
+    double *d_part0 = nullptr, *d_part1 = nullptr;
+    int part_cap = 0;
+    CgState* d_state = nullptr;
+    unsigned long long* d_counts = nullptr;
+    long long launches = 0;
+
+    Solver(int r, int c, int k, int o) : rows(r), cols(c), K(k), op(o) {
+        pitch = round_up(cols, 32);
+        plane = (long long)rows * pitch;
+    }
+
+    ~Solver() override {
+        cudaFree(d_flags); cudaFree(d_soft); cudaFree(d_dinv);
+        cudaFree(d_x); cudaFree(d_b); cudaFree(d_r); cudaFree(d_p); cudaFree(d_q);
+        for (auto& p : d_stage) cudaFree(p);
+        cudaFree(d_out); cudaFree(d_part0); cudaFree(d_part1); cudaFree(d_state); cudaFree(d_counts);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    int init() {
+        CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&ev0));
+        CU(cudaEventCreate(&ev1));
+        CU(cudaMalloc(&d_flags, plane));
+        CU(cudaMalloc(&d_state, sizeof(CgState)));
+        CU(cudaMalloc(&d_counts, 4 * sizeof(unsigned long long)));
+        return HG_OK;
+    }
+
+    Grid<T> grid() const {
+        Grid<T> g;
+        g.rows = rows; g.cols = cols; g.pitch = pitch; g.plane = plane; g.K = K;
+        g.flags = d_flags; g.soft = d_soft; g.soft_scalar = (T)soft_scalar; g.w_g = (T)w_g;
+        return g;
+    }
+
+    // ---- grid geometry of the operator launch ------------------------------------------
+    dim3 op_grid() const {
+        if (op == HG_OP_LAPLACIAN) return dim3((pitch / 4 + LAP_TX - 1) / LAP_TX, (rows + LAP_ROWS - 1) / LAP_ROWS);
+        return dim3((pitch + BilapTile<T>::TX - 1) / BilapTile<T>::TX, (rows + BilapTile<T>::TY - 1) / BilapTile<T>::TY);
+    }
+    int op_blocks() const { dim3 g = op_grid(); return g.x * g.y; }
+    int vec_blocks() const {
+        long long n4 = plane / 4;
+        long long nb = (n4 + VEC_THREADS - 1) / VEC_THREADS;
+        return (int)std::min<long long>(nb, 148 * 8);
+    }
+
+    template <int MODE, int DOT>
+    void launch_op(const T* x, const T* b, T* y, double* partial, const int* done) {
+        const Grid<T> g = grid();
+        if (op == HG_OP_LAPLACIAN)
+            lap_apply_kernel<T, MODE, DOT><<<op_grid(), LAP_TX, 0, stream>>>(g, x, b, y, partial, done);
+        else
+            bilap_apply_kernel<T, MODE, DOT><<<op_grid(), BILAP_THREADS, 0, stream>>>(g, x, b, y, partial, done);
+        ++launches;
+    }
+
+    int set_flags(const uint8_t* f) override {
+        if (!f) return fail(HG_ERR_INVALID, "hg_set_flags: NULL flags");
+        // sanitise on the way in: edge bits that point outside the grid are dropped, padding is hard
+        std::vector<uint8_t> tmp((size_t)plane, (uint8_t)HG_FLAG_HARD);
+        for (int i = 0; i < rows; ++i) {
+            uint8_t* dst = tmp.data() + (size_t)i * pitch;
+            memcpy(dst, f + (size_t)i * cols, cols);
+            if (i == rows - 1)
+                for (int j = 0; j < cols; ++j) dst[j] &= ~(HG_FLAG_CUT_DOWN | HG_FLAG_PEN_DOWN);
+            dst[cols - 1] &= ~(HG_FLAG_CUT_RIGHT | HG_FLAG_PEN_RIGHT);
+        }
+        CU(cudaMemcpyAsync(d_flags, tmp.data(), plane, cudaMemcpyHostToDevice, stream));
+        CU(cudaStreamSynchronize(stream));
+        flags_set = true;
+        is_setup = false;
+        return HG_OK;
+    }
+
+    int set_soft(const double* w, double scalar) override {
+        soft_scalar = scalar;
+        if (!w) {
+            cudaFree(d_soft);
+            d_soft = nullptr;
+            soft_plane_set = false;
+        } else {
+            std::vector<T> tmp((size_t)plane, T(0));
+            for (int i = 0; i < rows; ++i)
+                for (int j = 0; j < cols; ++j) tmp[(size_t)i * pitch + j] = (T)w[(size_t)i * cols + j];
+            if (!d_soft) CU(cudaMalloc(&d_soft, plane * sizeof(T)));
+            CU(cudaMemcpyAsync(d_soft, tmp.data(), plane * sizeof(T), cudaMemcpyHostToDevice, stream));
+            CU(cudaStreamSynchronize(stream));
+            soft_plane_set = true;
+        }
+        is_setup = false;
+        return HG_OK;
+    }
+
+    int set_grad_weight(double w) override {
+        w_g = w;
+        is_setup = false;
+        return HG_OK;
+    }
+
+    int set_precond(int p) override {
+        if (p != HG_PRECOND_JACOBI && p != HG_PRECOND_MULTIGRID) return fail(HG_ERR_INVALID, "unknown preconditioner");
+        precond = p;
+        is_setup = false;
+        return HG_OK;
+    }
+
+    int ensure_vectors() {
+        const size_t bytes = (size_t)plane * K * sizeof(T);
+        T** v[] = {&d_x, &d_b, &d_r, &d_p, &d_q};
+        for (T** p : v)
+            if (!*p) {
+                CU(cudaMalloc(p, bytes));
+                CU(cudaMemsetAsync(*p, 0, bytes, stream));
+            }
+        if (!d_dinv) CU(cudaMalloc(&d_dinv, plane * sizeof(T)));
+        const int need = std::max(op_blocks(), vec_blocks()) * K;
+        if (need > part_cap) {
+            cudaFree(d_part0); cudaFree(d_part1);
+            d_part0 = d_part1 = nullptr;
+            CU(cudaMalloc(&d_part0, (size_t)need * sizeof(double)));
+            CU(cudaMalloc(&d_part1, (size_t)need * sizeof(double)));
+            part_cap = need;
+        }
+        return HG_OK;
+    }
+
+    int setup(hg_setup_info* info) override {
+        if (!flags_set) return fail(HG_ERR_INVALID, "hg_setup: hg_set_flags has not been called");
+        CU(cudaEventRecord(ev0, stream));
+        HGTRY(ensure_vectors());
+        CU(cudaMemsetAsync(d_counts, 0, 4 * sizeof(unsigned long long), stream));
+        dim3 pg((pitch + 255) / 256, rows);
+        domain_check_kernel<<<pg, 256, 0, stream>>>(d_flags, rows, cols, pitch, op == HG_OP_BILAPLACIAN, d_counts);
+        diag_kernel<T><<<pg, 256, 0, stream>>>(grid(), op == HG_OP_BILAPLACIAN, d_dinv);
+        unsigned long long counts[4];
+        CU(cudaMemcpyAsync(counts, d_counts, sizeof counts, cudaMemcpyDeviceToHost, stream));
+        CU(cudaEventRecord(ev1, stream));
+        CU(cudaStreamSynchronize(stream));
+        CU(cudaGetLastError());
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ev0, ev1));
+        if (info) {
+            info->levels = 1;
+            info->empty_rows = (int)counts[0];
+            info->unreferenced = (int)counts[1];
+            info->n_hard = (long long)counts[2];
+            info->n_free = (long long)rows * cols - (long long)counts[2];
+            info->setup_ms = ms;
+        }
+        if (op == HG_OP_BILAPLACIAN) {
+            // recovery.py:493 and :495
+            const int expect = (rows == 1 || cols == 1) ? 2 : 4;
+            if ((int)counts[0] != expect && counts[3] == 0)
+                return fail(HG_ERR_EMPTY_ROWS, "bilaplacian: unexpected number of empty rows in the reflected Laplacian (recovery.py:493)");
+            if (counts[1] != 0)
+                return fail(HG_ERR_UNREFERENCED, "bilaplacian: a pixel is referenced by no row of the reflected Laplacian (recovery.py:495)");
+        }
+        is_setup = true;
+        return HG_OK;
+    }
+
+    int stage(int slot, const double* host) {
+        const size_t bytes = (size_t)rows * cols * K * sizeof(double);
+        if (!host) return HG_OK;
+        if (!d_stage[slot]) CU(cudaMalloc(&d_stage[slot], bytes));
+        CU(cudaMemcpyAsync(d_stage[slot], host, bytes, cudaMemcpyHostToDevice, stream));
+        return HG_OK;
+    }
+
+    int apply(const double* x, double* y) override {
+        if (!is_setup) return fail(HG_ERR_INVALID, "hg_apply: hg_setup has not been called");
+        if (!x || !y) return fail(HG_ERR_INVALID, "hg_apply: NULL buffer");
+        HGTRY(stage(0, x));
+        const size_t bytes = (size_t)rows * cols * K * sizeof(double);
+        if (!d_out) CU(cudaMalloc(&d_out, bytes));
+        dim3 pg((pitch + 255) / 256, rows);
+        import_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_stage[0], d_p);
+        launch_op<0, 0>(d_p, nullptr, d_q, nullptr, nullptr);
+        export_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_q, d_out);
+        CU(cudaMemcpyAsync(y, d_out, bytes, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        CU(cudaGetLastError());
+        have_values = false;
+        return HG_OK;
+    }
+
+    int upload(const hg_values* v, hg_stats* st) override {
+        if (!is_setup) return fail(HG_ERR_INVALID, "hg_upload_values: hg_setup has not been called");
+        hg_values z;
+        memset(&z, 0, sizeof z);
+        if (!v) v = &z;
+        CU(cudaEventRecord(ev0, stream));
+        const double* host[5] = {v->hard_vals, v->soft_vals, v->d_down, v->d_right, v->x0};
+        for (int s = 0; s < 5; ++s) HGTRY(stage(s, host[s]));
+        dim3 pg((pitch + 255) / 256, rows);
+        build_problem_kernel<T><<<pg, 256, 0, stream>>>(grid(), host[0] ? d_stage[0] : nullptr, host[1] ? d_stage[1] : nullptr,
+                                                       host[2] ? d_stage[2] : nullptr, host[3] ? d_stage[3] : nullptr,
+                                                       host[4] ? d_stage[4] : nullptr, d_x, d_b);
+        CU(cudaEventRecord(ev1, stream));
+        CU(cudaStreamSynchronize(stream));
+        CU(cudaGetLastError());
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ev0, ev1));
+        if (st) st->upload_ms = ms;
+        have_values = true;
+        return HG_OK;
+    }
+
+    // One PCG solve on device-resident x (hard values + initial guess) and b.
+    int solve_device(double rtol, int maxiter, hg_stats* st) override {
+        if (!is_setup || !have_values) return fail(HG_ERR_INVALID, "hg_solve_device: values have not been uploaded");
+        if (maxiter <= 0) maxiter = 100000;
+        launches = 0;
+        const int nb_op = op_blocks(), nb_vec = vec_blocks();
+        CgState init;
+        memset(&init, 0, sizeof init);
+        init.tol2 = rtol * rtol;
+        init.maxiter = maxiter;
+        CU(cudaMemcpyAsync(d_state, &init, sizeof init, cudaMemcpyHostToDevice, stream));
+        CU(cudaEventRecord(ev0, stream));
+        int* done = &d_state->done;
+
+        // r = b - F(x0);  bb = r.r;  z = dinv r;  rz = r.z;  p = z
+        launch_op<1, 0>(d_x, d_b, d_r, nullptr, nullptr);
+        cg_norms_jacobi_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(plane, K, d_r, d_dinv, d_part0, d_part1);
+        cg_beta_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, d_part1, nb_vec, K, 1);
+        cg_pupdate_jacobi_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_p, d_r, d_dinv);
+        launches += 3;
+
+        CgState host;
+        int it = 0;
+        const int batch = 32;
+        while (true) {
+            const int n = std::min(batch, maxiter - it);
+            for (int s = 0; s < n; ++s) {
+                launch_op<0, 1>(d_p, nullptr, d_q, d_part0, done);
+                cg_alpha_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_op, K);
+                cg_update_jacobi_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_x, d_r, d_p, d_q, d_dinv, d_part0, d_part1);
+                cg_beta_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, d_part1, nb_vec, K, 0);
+                cg_pupdate_jacobi_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_p, d_r, d_dinv);
+                launches += 4;
+            }
+            it += n;
+            CU(cudaMemcpyAsync(&host, d_state, sizeof host, cudaMemcpyDeviceToHost, stream));
+            CU(cudaStreamSynchronize(stream));
+            if (host.done || it >= maxiter) break;
+        }
+        // true residual of the reduced system, from scratch
+        launch_op<1, 2>(d_x, d_b, d_q, d_part0, nullptr);
+        std::vector<double> part((size_t)nb_op * K);
+        CU(cudaMemcpyAsync(part.data(), d_part0, part.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CU(cudaEventRecord(ev1, stream));
+        CU(cudaStreamSynchronize(stream));
+        CU(cudaGetLastError());
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ev0, ev1));
+
+        double relres = 0.0, relres_cg = 0.0;
+        for (int k = 0; k < K; ++k) {
+            double s = 0.0;
+            for (int i = 0; i < nb_op; ++i) s += part[(size_t)k * nb_op + i];
+            if (host.bb[k] > 0.0) {
+                relres = std::max(relres, sqrt(s / host.bb[k]));
+                relres_cg = std::max(relres_cg, sqrt(host.rr[k] / host.bb[k]));
+            }
+        }
+        int status = HG_OK;
+        if (host.done == 2 || relres != relres) status = HG_ERR_BREAKDOWN;
+        else if (host.done == 0) status = HG_ERR_NOT_CONVERGED;
+        if (st) {
+            st->iterations = host.iter;
+            st->status = status;
+            st->relres = relres;
+            st->relres_cg = relres_cg;
+            st->solve_ms = ms;
+            st->launches = launches;
+            const double W = sizeof(T);
+            const double npx = (double)rows * cols;
+            // un-preconditioned CG iteration: K*11W + 1 bytes per pixel (+ W for the Jacobi diagonal, read twice)
+            st->bytes_moved = npx * ((double)host.iter * (K * 11.0 * W + 1.0 + 2.0 * W) + 2.0 * (K * 3.0 * W + 1.0));
+        }
+        if (status == HG_ERR_BREAKDOWN) return fail(status, "conjugate gradients broke down (NaN or non-positive curvature): singular or under-constrained system");
+        if (status == HG_ERR_NOT_CONVERGED) return fail(status, "conjugate gradients did not reach the requested tolerance within maxiter");
+        return HG_OK;
+    }
+
+    int download(double* x, hg_stats* st) override {
+        if (!x) return fail(HG_ERR_INVALID, "hg_download: NULL buffer");
+        const size_t bytes = (size_t)rows * cols * K * sizeof(double);
+        if (!d_out) CU(cudaMalloc(&d_out, bytes));
+        CU(cudaEventRecord(ev0, stream));
+        dim3 pg((pitch + 255) / 256, rows);
+        export_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_x, d_out);
+        CU(cudaMemcpyAsync(x, d_out, bytes, cudaMemcpyDeviceToHost, stream));
+        CU(cudaEventRecord(ev1, stream));
+        CU(cudaStreamSynchronize(stream));
+        CU(cudaGetLastError());
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ev0, ev1));
+        if (st) st->download_ms = ms;
+        return HG_OK;
+    }
+
+    int bench_apply(int iters, double* ms_out) override {
+        if (!is_setup) return fail(HG_ERR_INVALID, "hg_bench_apply: hg_setup has not been called");
+        if (iters <= 0) iters = 1;
+        for (int w = 0; w < 3; ++w) launch_op<0, 0>(d_p, nullptr, d_q, nullptr, nullptr);
+        CU(cudaEventRecord(ev0, stream));
+        for (int s = 0; s < iters; ++s) launch_op<0, 0>(d_p, nullptr, d_q, nullptr, nullptr);
+        CU(cudaEventRecord(ev1, stream));
+        CU(cudaStreamSynchronize(stream));
+        CU(cudaGetLastError());
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ev0, ev1));
+        if (ms_out) *ms_out = ms / iters;
+        return HG_OK;
+    }
+};
+
+}  // namespace hg
+
+using namespace hg;
+
+struct hg_solver {
+    SolverBase* impl;
+};
+
+extern "C" {
+
+int hg_version(void) { return HGRID_VERSION; }
+
+const char* hg_last_error(void) { return g_err.c_str(); }
+
+int hg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int hg_create(int rows, int cols, int channels, int op, int precision, hg_handle* out) {
+    if (!out) return fail(HG_ERR_INVALID, "hg_create: NULL out");
+    *out = nullptr;
+    if (rows <= 0 || cols <= 0) return fail(HG_ERR_INVALID, "hg_create: rows and cols must be positive");
+    if (channels <= 0 || channels > HG_MAXK) return fail(HG_ERR_INVALID, "hg_create: channels must be in 1..16");
+    if (op != HG_OP_LAPLACIAN && op != HG_OP_BILAPLACIAN) return fail(HG_ERR_INVALID, "hg_create: unknown operator");
+    if (precision != HG_PREC_FP32 && precision != HG_PREC_FP64) return fail(HG_ERR_INVALID, "hg_create: unknown precision");
+    if (hg_device_count() <= 0) return fail(HG_ERR_NO_DEVICE, "hg_create: no CUDA device is visible; libhgrid has no CPU path");
+    SolverBase* s = nullptr;
+    int rc;
+    if (precision == HG_PREC_FP32) {
+        auto* p = new (std::nothrow) Solver<float>(rows, cols, channels, op);
+        if (!p) return fail(HG_ERR_NOMEM, "out of host memory");
+        rc = p->init();
+        s = p;
+    } else {
+        auto* p = new (std::nothrow) Solver<double>(rows, cols, channels, op);
+        if (!p) return fail(HG_ERR_NOMEM, "out of host memory");
+        rc = p->init();
+        s = p;
+    }
+    if (rc != HG_OK) {
+        delete s;
+        return rc;
+    }
+    hg_solver* h = new hg_solver;
+    h->impl = s;
+    *out = h;
+    return HG_OK;
+}
+
+int hg_destroy(hg_handle h) {
+    if (!h) return HG_OK;
+    delete h->impl;
+    delete h;
+    return HG_OK;
+}
+
+#define CHECK_H(h) \
+    if (!(h) || !(h)->impl) return fail(HG_ERR_INVALID, "NULL solver handle")
+
+int hg_set_flags(hg_handle h, const uint8_t* flags) { CHECK_H(h); return h->impl->set_flags(flags); }
+int hg_set_soft_weights(hg_handle h, const double* w, double scalar_w) { CHECK_H(h); return h->impl->set_soft(w, scalar_w); }
+int hg_set_grad_weight(hg_handle h, double w_g) { CHECK_H(h); return h->impl->set_grad_weight(w_g); }
+int hg_set_preconditioner(hg_handle h, int p) { CHECK_H(h); return h->impl->set_precond(p); }
+int hg_setup(hg_handle h, hg_setup_info* info) { CHECK_H(h); return h->impl->setup(info); }
+int hg_apply(hg_handle h, const double* x, double* y) { CHECK_H(h); return h->impl->apply(x, y); }
+int hg_upload_values(hg_handle h, const hg_values* v, hg_stats* st) { CHECK_H(h); return h->impl->upload(v, st); }
+int hg_solve_device(hg_handle h, double rtol, int maxiter, hg_stats* st) { CHECK_H(h); return h->impl->solve_device(rtol, maxiter, st); }
+int hg_download(hg_handle h, double* x, hg_stats* st) { CHECK_H(h); return h->impl->download(x, st); }
+int hg_bench_apply(hg_handle h, int iters, double* ms) { CHECK_H(h); return h->impl->bench_apply(iters, ms); }
+
+int hg_solve(hg_handle h, const hg_values* vals, double* x_out, double rtol, int maxiter, hg_stats* stats) {
+    CHECK_H(h);
+    hg_stats local;
+    memset(&local, 0, sizeof local);
+    hg_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof *st);
+    HGTRY(h->impl->upload(vals, st));
+    int rc = h->impl->solve_device(rtol, maxiter, st);
+    // the iterate is returned even if the tolerance was not reached; the caller decides
+    if (rc != HG_OK && rc != HG_ERR_NOT_CONVERGED) return rc;
+    HGTRY(h->impl->download(x_out, st));
+    return rc;
+}
+
+}  // extern "C"

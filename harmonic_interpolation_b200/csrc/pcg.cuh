@@ -1,0 +1,245 @@
+// pcg.cuh -- conjugate-gradient vector kernels with device-resident scalars.
+//
+// The K channels are K independent systems sharing one operator; they are advanced in
+// lock step by the same launches, each with its own alpha / beta.  No scalar ever visits
+// the host inside the iteration: reductions leave per-block fp64 partial sums, a
+// one-block "scalar stage" adds them in a fixed order and forms alpha / beta, and every
+// kernel returns immediately once CgState::done is set, so the host can enqueue
+// iterations in batches and look at the state only between batches.
+#pragma once
+#include "common.cuh"
+
+namespace hg {
+
+struct CgState {
+    double rz[HG_MAXK];     // r.z of the current iteration
+    double pq[HG_MAXK];     // p.Ap
+    double rr[HG_MAXK];     // r.r
+    double bb[HG_MAXK];     // ||b_f - A_fc x_c||^2, the reference norm of the stopping rule
+    double alpha[HG_MAXK];
+    double beta[HG_MAXK];
+    double tol2;            // rtol^2
+    int iter;
+    int done;               // 1 converged, 2 breakdown
+    int maxiter;
+};
+
+// Adds `n` partial sums per channel in a fixed order (one block).
+__device__ __forceinline__ double ordered_sum(const double* part, int n, double* red) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
+    return block_sum(s, red);
+}
+
+// after q = A p:  alpha = rz / pq
+__global__ void cg_alpha_kernel(CgState* st, const double* __restrict__ part_pq, int nblk, int K) {
+    if (st->done) return;
+    __shared__ double red[32];
+    for (int k = 0; k < K; ++k) {
+        const double pq = ordered_sum(part_pq + (long long)k * nblk, nblk, red);
+        if (threadIdx.x == 0) {
+            st->pq[k] = pq;
+            double a = 0.0;
+            if (st->rz[k] != 0.0) {
+                if (!(pq > 0.0)) st->done = 2;  // NaN or non-positive curvature
+                else a = st->rz[k] / pq;
+            }
+            st->alpha[k] = a;
+        }
+        __syncthreads();
+    }
+}
+
+// after the x / r update: rr, rz_new -> beta, convergence test, iteration count.
+// part_rr / part_rz hold nblk partial sums per channel.
+__global__ void cg_beta_kernel(CgState* st, const double* __restrict__ part_rr, const double* __restrict__ part_rz,
+                               int nblk, int K, int init) {
+    if (st->done) return;
+    __shared__ double red[32];
+    __shared__ int all_conv;
+    if (threadIdx.x == 0) all_conv = 1;
+    __syncthreads();
+    for (int k = 0; k < K; ++k) {
+        const double rr = ordered_sum(part_rr + (long long)k * nblk, nblk, red);
+        const double rz = ordered_sum(part_rz + (long long)k * nblk, nblk, red);
+        if (threadIdx.x == 0) {
+            if (init) {
+                st->bb[k] = rr;
+                st->beta[k] = 0.0;
+            } else {
+                st->beta[k] = st->rz[k] != 0.0 ? rz / st->rz[k] : 0.0;
+            }
+            st->rr[k] = rr;
+            st->rz[k] = rz;
+            if (!(rr == rr) || !(rz == rz)) st->done = 2;
+            if (rr > st->tol2 * st->bb[k]) all_conv = 0;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (!init) st->iter += 1;
+        if (all_conv && st->done == 0) st->done = 1;
+    }
+}
+
+#define VEC_THREADS 256
+
+// x += alpha p ; r -= alpha q ; partial sums of r.r and of r.(dinv r)   (Jacobi: z = dinv r)
+template <typename T>
+__global__ void __launch_bounds__(VEC_THREADS)
+cg_update_jacobi_kernel(const CgState* __restrict__ st, long long plane, int K, T* __restrict__ x, T* __restrict__ r,
+                        const T* __restrict__ p, const T* __restrict__ q, const T* __restrict__ dinv,
+                        double* __restrict__ part_rr, double* __restrict__ part_rz) {
+    if (st->done) return;
+    __shared__ double red[32];
+    const long long n4 = plane >> 2;
+    for (int k = 0; k < K; ++k) {
+        const T a = (T)st->alpha[k];
+        T* xk = x + k * plane; T* rk = r + k * plane;
+        const T* pk = p + k * plane; const T* qk = q + k * plane;
+        double srr = 0.0, srz = 0.0;
+        for (long long v = (long long)blockIdx.x * VEC_THREADS + threadIdx.x; v < n4; v += (long long)gridDim.x * VEC_THREADS) {
+            const long long o = v << 2;
+            V4<T> xv = ld4(xk + o), rv = ld4(rk + o);
+            const V4<T> pv = ld4(pk + o), qv = ld4(qk + o), dv = ld4(dinv + o);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                xv.v[c] += a * pv.v[c];
+                rv.v[c] -= a * qv.v[c];
+                const double rd = (double)rv.v[c];
+                srr += rd * rd;
+                srz += rd * rd * (double)dv.v[c];
+            }
+            st4(xk + o, xv);
+            st4(rk + o, rv);
+        }
+        const double s1 = block_sum(srr, red);
+        const double s2 = block_sum(srz, red);
+        if (threadIdx.x == 0) {
+            part_rr[(long long)k * gridDim.x + blockIdx.x] = s1;
+            part_rz[(long long)k * gridDim.x + blockIdx.x] = s2;
+        }
+    }
+}
+
+// partial sums of r.r and r.(dinv r) without an update (initial residual)
+template <typename T>
+__global__ void __launch_bounds__(VEC_THREADS)
+cg_norms_jacobi_kernel(long long plane, int K, const T* __restrict__ r, const T* __restrict__ dinv,
+                       double* __restrict__ part_rr, double* __restrict__ part_rz) {
+    __shared__ double red[32];
+    const long long n4 = plane >> 2;
+    for (int k = 0; k < K; ++k) {
+        const T* rk = r + k * plane;
+        double srr = 0.0, srz = 0.0;
+        for (long long v = (long long)blockIdx.x * VEC_THREADS + threadIdx.x; v < n4; v += (long long)gridDim.x * VEC_THREADS) {
+            const long long o = v << 2;
+            const V4<T> rv = ld4(rk + o), dv = ld4(dinv + o);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const double rd = (double)rv.v[c];
+                srr += rd * rd;
+                srz += rd * rd * (double)dv.v[c];
+            }
+        }
+        const double s1 = block_sum(srr, red);
+        const double s2 = block_sum(srz, red);
+        if (threadIdx.x == 0) {
+            part_rr[(long long)k * gridDim.x + blockIdx.x] = s1;
+            part_rz[(long long)k * gridDim.x + blockIdx.x] = s2;
+        }
+    }
+}
+
+// p = dinv r + beta p     (Jacobi)
+template <typename T>
+__global__ void __launch_bounds__(VEC_THREADS)
+cg_pupdate_jacobi_kernel(const CgState* __restrict__ st, long long plane, int K, T* __restrict__ p,
+                         const T* __restrict__ r, const T* __restrict__ dinv) {
+    if (st->done) return;
+    const long long n4 = plane >> 2;
+    for (int k = 0; k < K; ++k) {
+        const T bt = (T)st->beta[k];
+        T* pk = p + k * plane; const T* rk = r + k * plane;
+        for (long long v = (long long)blockIdx.x * VEC_THREADS + threadIdx.x; v < n4; v += (long long)gridDim.x * VEC_THREADS) {
+            const long long o = v << 2;
+            V4<T> pv = ld4(pk + o);
+            const V4<T> rv = ld4(rk + o), dv = ld4(dinv + o);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) pv.v[c] = dv.v[c] * rv.v[c] + bt * pv.v[c];
+            st4(pk + o, pv);
+        }
+    }
+}
+
+// ---- host <-> device value conversion ---------------------------------------------------
+// Host arrays are (rows, cols, K) float64 with K innermost; device planes are K planes of
+// pitch-strided T.  build_problem_kernel forms, in one pass over the staged host arrays,
+//   x   = hard value at hard pixels, x0 (or 0) at free pixels
+//   b   = s_p v_p + w_g [ d_down(up) - d_down(p) + d_right(left) - d_right(p) ]  at free pixels
+// (C^T W Crhs of recovery.py:927, 1321; +w d at the far endpoint, -w d at (i,j)).
+template <typename T>
+__global__ void build_problem_kernel(Grid<T> g, const double* __restrict__ hard_vals, const double* __restrict__ soft_vals,
+                                     const double* __restrict__ d_down, const double* __restrict__ d_right,
+                                     const double* __restrict__ x0, T* __restrict__ x, T* __restrict__ b) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= g.pitch) return;
+    const long long o = (long long)i * g.pitch + j;
+    const int K = g.K;
+    if (j >= g.cols) {
+        for (int k = 0; k < K; ++k) { x[k * g.plane + o] = T(0); b[k * g.plane + o] = T(0); }
+        return;
+    }
+    const long long h = ((long long)i * g.cols + j) * K;  // host offset
+    const unsigned f = g.flags[o];
+    if (f & HG_FLAG_HARD) {
+        for (int k = 0; k < K; ++k) {
+            x[k * g.plane + o] = hard_vals ? (T)hard_vals[h + k] : T(0);
+            b[k * g.plane + o] = T(0);
+        }
+        return;
+    }
+    const unsigned fu = i > 0 ? g.flags[o - g.pitch] : 0u;
+    const unsigned fl = j > 0 ? g.flags[o - 1] : 0u;
+    const double sw = (double)soft_w(g, o, f);
+    const double wg = (double)g.w_g;
+    const bool pd = d_down && (f & HG_FLAG_PEN_DOWN) && i + 1 < g.rows;
+    const bool pr = d_right && (f & HG_FLAG_PEN_RIGHT) && j + 1 < g.cols;
+    const bool pu = d_down && i > 0 && (fu & HG_FLAG_PEN_DOWN);
+    const bool pl = d_right && j > 0 && (fl & HG_FLAG_PEN_RIGHT);
+    for (int k = 0; k < K; ++k) {
+        double v = 0.0;
+        if (sw != 0.0 && soft_vals) v += sw * soft_vals[h + k];
+        if (pd) v -= wg * d_down[h + k];
+        if (pr) v -= wg * d_right[h + k];
+        if (pu) v += wg * d_down[h - (long long)g.cols * K + k];
+        if (pl) v += wg * d_right[h - K + k];
+        b[k * g.plane + o] = (T)v;
+        x[k * g.plane + o] = x0 ? (T)x0[h + k] : T(0);
+    }
+}
+
+// planar T -> (rows, cols, K) float64
+template <typename T>
+__global__ void export_kernel(Grid<T> g, const T* __restrict__ x, double* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= g.cols) return;
+    const long long o = (long long)i * g.pitch + j;
+    const long long h = ((long long)i * g.cols + j) * g.K;
+    for (int k = 0; k < g.K; ++k) out[h + k] = (double)x[k * g.plane + o];
+}
+
+// (rows, cols, K) float64 -> planar T (padding zeroed)
+template <typename T>
+__global__ void import_kernel(Grid<T> g, const double* __restrict__ in, T* __restrict__ x) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= g.pitch) return;
+    const long long o = (long long)i * g.pitch + j;
+    const long long h = ((long long)i * g.cols + j) * g.K;
+    for (int k = 0; k < g.K; ++k) x[k * g.plane + o] = j < g.cols ? (T)in[h + k] : T(0);
+}
+
+}  // namespace hg

@@ -1,0 +1,158 @@
+"""Array-native interface to libhgrid.so.
+
+A `GridSolver` is the device-resident counterpart of the reference's factor-once closure
+(recovery.py:1304-1336): the constraint *pattern* (which pixels are hard / soft, which
+edges are cut or carry a gradient constraint, the weights) is fixed at construction and
+uploaded once; `solve()` may then be called with any number of value sets.
+"""
+import ctypes
+import os
+import weakref
+
+import numpy as np
+
+from . import _capi as C
+
+
+def default_precision():
+    """'fp64' unless HGRID_PRECISION=fp32.  The drop-in entry points default to fp64 so that
+    results agree with the reference's float64 direct solve to ~1e-9 of the value range."""
+    p = os.environ.get("HGRID_PRECISION", "fp64").lower()
+    assert p in ("fp32", "fp64")
+    return p
+
+
+def default_rtol(precision):
+    v = os.environ.get("HGRID_RTOL")
+    if v is not None:
+        return float(v)
+    return 1e-12 if precision == "fp64" else 1e-7
+
+
+def encode_flags(rows, cols, hard=None, soft=None, cut_down=None, cut_right=None, pen_down=None, pen_right=None):
+    """Boolean (rows, cols) planes -> one flag byte per pixel (include/hgrid.h)."""
+    f = np.zeros((rows, cols), np.uint8)
+    for plane, bit in ((hard, C.FLAG_HARD), (cut_down, C.FLAG_CUT_DOWN), (cut_right, C.FLAG_CUT_RIGHT),
+                       (pen_down, C.FLAG_PEN_DOWN), (pen_right, C.FLAG_PEN_RIGHT), (soft, C.FLAG_SOFT)):
+        if plane is not None:
+            plane = np.asarray(plane, dtype=bool)
+            assert plane.shape == (rows, cols)
+            f |= plane.astype(np.uint8) * np.uint8(bit)
+    # hard wins over soft at the same pixel (recovery.py:1286-1290)
+    f[(f & C.FLAG_HARD) != 0] &= np.uint8(~C.FLAG_SOFT & 0xFF)
+    return f
+
+
+class GridSolver:
+    def __init__(self, rows, cols, channels=1, bilaplacian=False, precision=None, preconditioner=None):
+        self.rows, self.cols, self.K = int(rows), int(cols), int(channels)
+        self.bilaplacian = bool(bilaplacian)
+        self.precision = precision or default_precision()
+        assert self.precision in ("fp32", "fp64")
+        self._lib = C.lib()
+        h = ctypes.c_void_p()
+        C.check(self._lib.hg_create(self.rows, self.cols, self.K,
+                                    C.OP_BILAPLACIAN if self.bilaplacian else C.OP_LAPLACIAN,
+                                    C.PREC_FP64 if self.precision == "fp64" else C.PREC_FP32, ctypes.byref(h)))
+        self._h = h
+        self._finalizer = weakref.finalize(self, self._lib.hg_destroy, h)
+        if preconditioner is None:
+            preconditioner = os.environ.get("HGRID_PRECOND", "jacobi")
+        C.check(self._lib.hg_set_preconditioner(self._h, {"jacobi": C.PRECOND_JACOBI, "multigrid": C.PRECOND_MULTIGRID}[preconditioner]))
+        self.flags = None
+        self.info = None
+        self.last_stats = None
+
+    def close(self):
+        self._finalizer()
+
+    # ---- pattern ------------------------------------------------------------------------
+    def set_pattern(self, flags, soft_weights=None, soft_scalar=0.0, w_g=0.0):
+        """flags: uint8 (rows, cols); soft_weights: float64 (rows, cols) per-pixel weights or None
+        (then `soft_scalar` applies to every FLAG_SOFT pixel); w_g: weight of FLAG_PEN_* edges."""
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        assert flags.shape == (self.rows, self.cols)
+        self.flags = flags
+        C.check(self._lib.hg_set_flags(self._h, flags.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))))
+        if soft_weights is not None:
+            soft_weights = np.ascontiguousarray(soft_weights, dtype=np.float64)
+            assert soft_weights.shape == (self.rows, self.cols)
+        C.check(self._lib.hg_set_soft_weights(self._h, C.dptr(soft_weights), float(soft_scalar)))
+        C.check(self._lib.hg_set_grad_weight(self._h, float(w_g)))
+        info = C.SetupInfo()
+        code = self._lib.hg_setup(self._h, ctypes.byref(info))
+        self.info = info
+        if code in (C.ERR_UNREFERENCED, C.ERR_EMPTY_ROWS):
+            # the reference raises AssertionError here (recovery.py:493, 495)
+            raise AssertionError(C.last_error())
+        C.check(code)
+        return info
+
+    # ---- values ---------------------------------------------------------------------------
+    def _vals(self, a):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if a.ndim == 2:
+            a = a[:, :, None]
+        assert a.shape == (self.rows, self.cols, self.K), (a.shape, (self.rows, self.cols, self.K))
+        return np.ascontiguousarray(a)
+
+    def apply(self, x):
+        """y = system * x at free pixels, 0 at hard pixels (hg_apply)."""
+        x = self._vals(x)
+        y = np.empty_like(x)
+        C.check(self._lib.hg_apply(self._h, C.dptr(x), C.dptr(y)))
+        return y
+
+    def solve(self, hard_vals=None, soft_vals=None, d_down=None, d_right=None, x0=None, rtol=None, maxiter=None,
+              allow_unconverged=False):
+        """Returns float64 (rows, cols, K).  Raises ArithmeticError if the iteration breaks down
+        (singular / under-constrained system; cvxopt raises ArithmeticError there too) or does
+        not converge (the reference asserts `0 == info`, recovery.py:972)."""
+        keep = [self._vals(a) for a in (hard_vals, soft_vals, d_down, d_right, x0)]
+        vals = C.Values(*[C.dptr(a) for a in keep])
+        out = np.empty((self.rows, self.cols, self.K), np.float64)
+        stats = C.Stats()
+        if rtol is None:
+            rtol = default_rtol(self.precision)
+        if maxiter is None:
+            maxiter = int(os.environ.get("HGRID_MAXITER", 0)) or max(2000, 40 * (self.rows + self.cols))
+        code = self._lib.hg_solve(self._h, ctypes.byref(vals), C.dptr(out), float(rtol), int(maxiter), ctypes.byref(stats))
+        self.last_stats = stats.as_dict()
+        if code == C.ERR_BREAKDOWN:
+            raise ArithmeticError(C.last_error())
+        if code == C.ERR_NOT_CONVERGED:
+            if not (allow_unconverged or os.environ.get("HGRID_ALLOW_UNCONVERGED")):
+                raise ArithmeticError("%s (relative residual %.3e after %d iterations)" % (
+                    C.last_error(), stats.relres, stats.iterations))
+        else:
+            C.check(code)
+        return out
+
+    # ---- three-step form used by bench.py ---------------------------------------------------
+    def upload(self, hard_vals=None, soft_vals=None, d_down=None, d_right=None, x0=None):
+        keep = [self._vals(a) for a in (hard_vals, soft_vals, d_down, d_right, x0)]
+        vals = C.Values(*[C.dptr(a) for a in keep])
+        stats = C.Stats()
+        C.check(self._lib.hg_upload_values(self._h, ctypes.byref(vals), ctypes.byref(stats)))
+        return stats.as_dict()
+
+    def solve_device(self, rtol, maxiter):
+        stats = C.Stats()
+        code = self._lib.hg_solve_device(self._h, float(rtol), int(maxiter), ctypes.byref(stats))
+        self.last_stats = stats.as_dict()
+        if code not in (C.OK, C.ERR_NOT_CONVERGED):
+            C.check(code)
+        return self.last_stats
+
+    def download(self):
+        out = np.empty((self.rows, self.cols, self.K), np.float64)
+        stats = C.Stats()
+        C.check(self._lib.hg_download(self._h, C.dptr(out), ctypes.byref(stats)))
+        return out, stats.as_dict()
+
+    def bench_apply(self, iters=20):
+        ms = ctypes.c_double()
+        C.check(self._lib.hg_bench_apply(self._h, int(iters), ctypes.byref(ms)))
+        return ms.value

@@ -1,0 +1,140 @@
+/*
+ * hgrid.h -- C ABI of libhgrid.so: B200 (sm_100a) grid-diffusion solver.
+ *
+ * This is the drop-in boundary for the hot path of yig/harmonic_interpolation.  The
+ * reference has no FFI seam: its seam is the Python module `recovery` (and
+ * `fill_alpha_harmonic`).  Each entry point below replaces a block of that module;
+ * the citation is file:line in the reference tree.  The Python side
+ * (harmonic_interpolation_b200/recovery.py) keeps the reference's call signatures and
+ * binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative hg_status on failure;
+ *     hg_last_error() returns a thread-local, human-readable description;
+ *   - plain pointers and sizes only, all host buffers caller-owned and C-contiguous;
+ *   - a grid has `rows` x `cols` pixels, row-major index p = i*cols + j
+ *     (recovery.py:254-256); value arrays are (rows, cols, K) with K innermost,
+ *     exactly the layout the reference returns (recovery.py:1078, 1329);
+ *   - one solver handle may be used by one thread at a time.
+ */
+#ifndef HGRID_H
+#define HGRID_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HGRID_VERSION 100
+
+typedef struct hg_solver* hg_handle;
+
+/* per-pixel flag byte (hg_set_flags) */
+enum {
+    HG_FLAG_HARD      = 1,  /* hard value constraint: recovery.py:647-777, 783-836            */
+    HG_FLAG_CUT_DOWN  = 2,  /* edge (i,j)-(i+1,j) is cut: recovery.py:309-319, 422-439        */
+    HG_FLAG_CUT_RIGHT = 4,  /* edge (i,j)-(i,j+1) is cut                                      */
+    HG_FLAG_PEN_DOWN  = 8,  /* dx constraint x[i+1,j]-x[i,j] = d: recovery.py:549-552, 926-927 */
+    HG_FLAG_PEN_RIGHT = 16, /* dy constraint x[i,j+1]-x[i,j] = d: recovery.py:554-557          */
+    HG_FLAG_SOFT      = 32  /* soft value constraint: recovery.py:559-562, 1280-1283          */
+};
+
+/* operator: recovery.py:909-913 */
+enum { HG_OP_LAPLACIAN = 0, HG_OP_BILAPLACIAN = 1 };
+
+/* arithmetic: fp32 storage with fp64 reductions, or fp64 throughout */
+enum { HG_PREC_FP32 = 0, HG_PREC_FP64 = 1 };
+
+/* preconditioner of the conjugate-gradient solve */
+enum { HG_PRECOND_JACOBI = 0, HG_PRECOND_MULTIGRID = 1 };
+
+typedef enum {
+    HG_OK = 0,
+    HG_ERR_INVALID = -1,       /* bad argument / call order                                         */
+    HG_ERR_CUDA = -2,          /* CUDA runtime failure                                              */
+    HG_ERR_NO_DEVICE = -3,     /* no CUDA device: there is no CPU fallback                          */
+    HG_ERR_UNREFERENCED = -4,  /* bilaplacian: a pixel is referenced by no row (recovery.py:495)    */
+    HG_ERR_EMPTY_ROWS = -5,    /* bilaplacian without cuts: wrong number of empty rows (:493)       */
+    HG_ERR_NOT_CONVERGED = -6, /* maxiter reached (the reference asserts info == 0, recovery.py:972) */
+    HG_ERR_BREAKDOWN = -7,     /* NaN / non-positive curvature: singular or under-constrained system */
+    HG_ERR_NOMEM = -8
+} hg_status;
+
+typedef struct {
+    int levels;          /* multigrid levels built (1 = none)              */
+    int empty_rows;      /* bilaplacian: rows of L_refl that are all zero  */
+    int unreferenced;    /* bilaplacian: pixels referenced by no row       */
+    long long n_free;    /* free (unknown) pixels                          */
+    long long n_hard;
+    double setup_ms;
+} hg_setup_info;
+
+/* host value arrays of one solve; each is (rows, cols, K) float64 or NULL (= zeros) */
+typedef struct {
+    const double* hard_vals; /* read where HG_FLAG_HARD   (recovery.py:756, 835)            */
+    const double* soft_vals; /* read where HG_FLAG_SOFT   (recovery.py:1321)                */
+    const double* d_down;    /* read where HG_FLAG_PEN_DOWN  (recovery.py:552)              */
+    const double* d_right;   /* read where HG_FLAG_PEN_RIGHT (recovery.py:557)              */
+    const double* x0;        /* optional initial guess on the free pixels                   */
+} hg_values;
+
+typedef struct {
+    int iterations;
+    int status;            /* hg_status of the solve                                        */
+    double relres;         /* max over channels of ||b_f - A_ff x_f|| / ||b_f||, recomputed  */
+    double relres_cg;      /* same, from the CG recurrence at exit                           */
+    double solve_ms;       /* device time of the solve proper (CUDA events)                  */
+    double upload_ms;      /* host -> device of the value arrays + conversion                */
+    double download_ms;    /* device -> host of the result                                   */
+    double bytes_moved;    /* algorithmic bytes of the solve (SURVEY 8(d) formulas)          */
+    long long launches;    /* kernels launched by the solve                                  */
+} hg_stats;
+
+int hg_version(void);
+const char* hg_last_error(void);
+int hg_device_count(void);
+
+/* Creates a solver for one rows x cols grid with K channels on the current CUDA device.
+ * Replaces the operator construction gen_symmetric_grid_laplacian (recovery.py:232-347)
+ * / gen_grid_laplacian2_with_boundary_reflection + L.T*L (recovery.py:349-500, 911). */
+int hg_create(int rows, int cols, int channels, int op, int precision, hg_handle* out);
+int hg_destroy(hg_handle h);
+
+/* rows*cols flag bytes.  Replaces the sparse constraint matrices of gen_constraint_system
+ * (recovery.py:504-573) and the cut-edge mask (recovery.py:309-319). */
+int hg_set_flags(hg_handle h, const uint8_t* flags);
+/* Per-pixel soft weights (rows*cols float64, read where HG_FLAG_SOFT) or NULL to use
+ * `scalar_w` for every HG_FLAG_SOFT pixel.  Replaces W = diag(w_lsq), C.T*W*C
+ * (recovery.py:1273-1283). */
+int hg_set_soft_weights(hg_handle h, const double* weights, double scalar_w);
+/* weight of the dx/dy constraints, w_gradients (recovery.py:875-884, 926-927) */
+int hg_set_grad_weight(hg_handle h, double w_g);
+int hg_set_preconditioner(hg_handle h, int precond);
+/* Validates the domain (recovery.py:484-495) and builds the device-resident operator
+ * and preconditioner.  Replaces the factorisation cvxopt.umfpack.numeric
+ * (recovery.py:1304); call once, then hg_solve any number of times. */
+int hg_setup(hg_handle h, hg_setup_info* info);
+
+/* y = system * x at free pixels, 0 at hard pixels; x, y are (rows, cols, K) float64.
+ * The matrix-free equivalent of `system * x` for the system of recovery.py:926, 1283. */
+int hg_apply(hg_handle h, const double* x, double* y);
+
+/* Solves for the grid.  Replaces rhs assembly + cvxopt.cholmod.linsolve / umfpack.solve
+ * (recovery.py:926-943, 993, 1059-1075, 1319-1327).  x_out is (rows, cols, K) float64. */
+int hg_solve(hg_handle h, const hg_values* vals, double* x_out, double rtol, int maxiter, hg_stats* stats);
+
+/* The same in three steps, so that a benchmark can time the device-resident solve. */
+int hg_upload_values(hg_handle h, const hg_values* vals, hg_stats* stats);
+int hg_solve_device(hg_handle h, double rtol, int maxiter, hg_stats* stats);
+int hg_download(hg_handle h, double* x_out, hg_stats* stats);
+
+/* Times `iters` launches of the stencil kernel on device-resident data (CUDA events on
+ * the solver's stream); returns mean milliseconds per launch. */
+int hg_bench_apply(hg_handle h, int iters, double* ms_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HGRID_H */
