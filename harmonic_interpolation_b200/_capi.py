@@ -57,6 +57,9 @@ SYMBOLS = {
     "hg_solve_device": (ctypes.c_int, [_H, ctypes.c_double, ctypes.c_int, ctypes.POINTER(Stats)]),
     "hg_download": (ctypes.c_int, [_H, _dp, ctypes.POINTER(Stats)]),
     "hg_bench_apply": (ctypes.c_int, [_H, ctypes.c_int, _dp]),
+    "hg_precond_apply": (ctypes.c_int, [_H, _dp, _dp]),
+    "hg_mg_levels": (ctypes.c_int, [_H]),
+    "hg_mg_get_level": (ctypes.c_int, [_H, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), _dp]),
 }
 
 _lib = None

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "mg.cuh"
 #include "pcg.cuh"
 #include "stencil.cuh"
 
@@ -50,6 +51,9 @@ struct SolverBase {
     virtual int solve_device(double rtol, int maxiter, hg_stats* st) = 0;
     virtual int download(double* x, hg_stats* st) = 0;
     virtual int bench_apply(int iters, double* ms) = 0;
+    virtual int mg_levels() = 0;
+    virtual int mg_get_level(int level, int* rows, int* cols, double* coef9) = 0;
+    virtual int precond_apply(const double* r, double* z) = 0;
 };
 
 template <typename T>
@@ -76,6 +80,11 @@ struct Solver : SolverBase {
     unsigned long long* d_counts = nullptr;
     long long launches = 0;
 
+    // multigrid hierarchy (levels >= 1; level 0 is the flag-encoded operator)
+    T* d_z = nullptr;
+    std::vector<Coarse<T>> coarse;
+    double* d_dense = nullptr;   // [A | A^-1] of the coarsest level
+
     Solver(int r, int c, int k, int o) : rows(r), cols(c), K(k), op(o) {
         pitch = round_up(cols, 32);
         plane = (long long)rows * pitch;
@@ -86,6 +95,8 @@ struct Solver : SolverBase {
         cudaFree(d_x); cudaFree(d_b); cudaFree(d_r); cudaFree(d_p); cudaFree(d_q);
         for (auto& p : d_stage) cudaFree(p);
         cudaFree(d_out); cudaFree(d_part0); cudaFree(d_part1); cudaFree(d_state); cudaFree(d_counts);
+        free_hierarchy();
+        cudaFree(d_z);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -200,6 +211,151 @@ struct Solver : SolverBase {
         return HG_OK;
     }
 
+
+    // ---- multigrid ----------------------------------------------------------------------------
+    void free_hierarchy() {
+        for (auto& c : coarse) { cudaFree(c.coef); cudaFree(c.x); cudaFree(c.b); }
+        coarse.clear();
+        cudaFree(d_dense);
+        d_dense = nullptr;
+    }
+
+    bool use_mg() const { return precond == HG_PRECOND_MULTIGRID && op == HG_OP_LAPLACIAN; }
+
+    int build_hierarchy() {
+        free_hierarchy();
+        if (!d_z) {
+            CU(cudaMalloc(&d_z, (size_t)plane * K * sizeof(T)));
+            CU(cudaMemsetAsync(d_z, 0, (size_t)plane * K * sizeof(T), stream));
+        }
+        int r = rows, c = cols;
+        while ((long long)r * c > 256) {
+            Coarse<T> L;
+            L.rows = (r + 1) / 2; L.cols = (c + 1) / 2;
+            L.pitch = round_up(L.cols, 32);
+            L.plane = (long long)L.rows * L.pitch;
+            L.K = K;
+            L.coef = L.x = L.b = nullptr;
+            CU(cudaMalloc(&L.coef, (size_t)L.plane * 9 * sizeof(T)));
+            CU(cudaMalloc(&L.x, (size_t)L.plane * K * sizeof(T)));
+            CU(cudaMalloc(&L.b, (size_t)L.plane * K * sizeof(T)));
+            CU(cudaMemsetAsync(L.x, 0, (size_t)L.plane * K * sizeof(T), stream));
+            CU(cudaMemsetAsync(L.b, 0, (size_t)L.plane * K * sizeof(T), stream));
+            dim3 cg((L.pitch + 127) / 128, L.rows);
+            if (coarse.empty()) {
+                FineAcc<T> fa{grid()};
+                galerkin_kernel<T, FineAcc<T>><<<cg, 128, 0, stream>>>(fa, L);
+            } else {
+                CoarseAcc<T> ca{coarse.back()};
+                galerkin_kernel<T, CoarseAcc<T>><<<cg, 128, 0, stream>>>(ca, L);
+            }
+            coarse.push_back(L);
+            r = L.rows; c = L.cols;
+        }
+        if (!coarse.empty()) {
+            const Coarse<T>& L = coarse.back();
+            const int n = L.rows * L.cols;
+            CU(cudaMalloc(&d_dense, (size_t)n * 2 * n * sizeof(double)));
+            dense_from_stencil_kernel<T><<<64, 256, 0, stream>>>(L, d_dense);
+            dense_fill_kernel<T><<<(n + 127) / 128, 128, 0, stream>>>(L, d_dense);
+            gauss_jordan_kernel<<<1, 1024, n * sizeof(double), stream>>>(d_dense, n);
+        }
+        CU(cudaGetLastError());
+        return HG_OK;
+    }
+
+    // z = M^-1 r : one V(1,1) cycle from a zero initial guess
+    void vcycle(T* z, const T* r, const int* done) {
+        FineAcc<T> fa{grid()};
+        const dim3 rb((cols / 2 + 1 + 255) / 256, rows);
+        cudaMemsetAsync(z, 0, (size_t)plane * K * sizeof(T), stream);
+        rbgs0_kernel<T><<<rb, 256, 0, stream>>>(fa, z, r, 0, done);
+        rbgs0_kernel<T><<<rb, 256, 0, stream>>>(fa, z, r, 1, done);
+        launches += 3;
+        const int nl = (int)coarse.size();
+        if (nl > 0) {
+            {
+                const Coarse<T>& L = coarse[0];
+                dim3 g((L.pitch + 255) / 256, L.rows);
+                resid_restrict_kernel<T, FineAcc<T>><<<g, 256, 0, stream>>>(fa, z, r, L, K, done);
+                ++launches;
+            }
+            for (int l = 0; l + 1 < nl; ++l) {
+                const Coarse<T>& L = coarse[l];
+                dim3 mg((L.cols / 2 + 1 + 255) / 256, (L.rows + 1) / 2);
+                for (int c = 0; c < 4; ++c) mcgs_kernel<T><<<mg, 256, 0, stream>>>(L, c, done);
+                const Coarse<T>& Lc = coarse[l + 1];
+                dim3 g((Lc.pitch + 255) / 256, Lc.rows);
+                CoarseAcc<T> ca{L};
+                resid_restrict_kernel<T, CoarseAcc<T>><<<g, 256, 0, stream>>>(ca, L.x, L.b, Lc, K, done);
+                launches += 5;
+            }
+            {
+                const Coarse<T>& L = coarse[nl - 1];
+                const int n = L.rows * L.cols;
+                coarsest_dense_kernel<T><<<K, 256, n * sizeof(double), stream>>>(L, d_dense, done);
+                ++launches;
+            }
+            for (int l = nl - 2; l >= 0; --l) {
+                const Coarse<T>& L = coarse[l];
+                CoarseAcc<T> ca{L};
+                dim3 g((L.cols + 255) / 256, L.rows);
+                prolong_add_kernel<T, CoarseAcc<T>><<<g, 256, 0, stream>>>(ca, L.x, coarse[l + 1], K, done);
+                dim3 mg((L.cols / 2 + 1 + 255) / 256, (L.rows + 1) / 2);
+                for (int c = 3; c >= 0; --c) mcgs_kernel<T><<<mg, 256, 0, stream>>>(L, c, done);
+                launches += 5;
+            }
+            dim3 g((cols + 255) / 256, rows);
+            prolong_add_kernel<T, FineAcc<T>><<<g, 256, 0, stream>>>(fa, z, coarse[0], K, done);
+            ++launches;
+        }
+        rbgs0_kernel<T><<<rb, 256, 0, stream>>>(fa, z, r, 1, done);
+        rbgs0_kernel<T><<<rb, 256, 0, stream>>>(fa, z, r, 0, done);
+        launches += 2;
+    }
+
+    int mg_levels() override { return 1 + (int)coarse.size(); }
+
+    int mg_get_level(int level, int* r_out, int* c_out, double* coef9) override {
+        if (level < 1 || level > (int)coarse.size()) return fail(HG_ERR_INVALID, "hg_mg_get_level: no such level");
+        const Coarse<T>& L = coarse[level - 1];
+        if (r_out) *r_out = L.rows;
+        if (c_out) *c_out = L.cols;
+        if (coef9) {
+            std::vector<T> tmp((size_t)L.plane * 9);
+            CU(cudaMemcpyAsync(tmp.data(), L.coef, tmp.size() * sizeof(T), cudaMemcpyDeviceToHost, stream));
+            CU(cudaStreamSynchronize(stream));
+            for (int c = 0; c < 9; ++c)
+                for (int i = 0; i < L.rows; ++i)
+                    for (int j = 0; j < L.cols; ++j)
+                        coef9[((size_t)i * L.cols + j) * 9 + c] = (double)tmp[(size_t)c * L.plane + (size_t)i * L.pitch + j];
+        }
+        return HG_OK;
+    }
+
+    // z = M^-1 r for host arrays (parity tests of the preconditioner: symmetry, definiteness)
+    int precond_apply(const double* r, double* z) override {
+        if (!is_setup) return fail(HG_ERR_INVALID, "hg_precond_apply: hg_setup has not been called");
+        HGTRY(stage(0, r));
+        const size_t bytes = (size_t)rows * cols * K * sizeof(double);
+        if (!d_out) CU(cudaMalloc(&d_out, bytes));
+        dim3 pg((pitch + 255) / 256, rows);
+        import_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_stage[0], d_r);
+        mask_hard_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_r);
+        if (use_mg()) {
+            vcycle(d_z, d_r, nullptr);
+            export_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_z, d_out);
+        } else {
+            jacobi_apply_kernel<T><<<vec_blocks(), VEC_THREADS, 0, stream>>>(plane, K, d_q, d_r, d_dinv);
+            export_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_q, d_out);
+        }
+        CU(cudaMemcpyAsync(z, d_out, bytes, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        CU(cudaGetLastError());
+        have_values = false;
+        return HG_OK;
+    }
+
     int setup(hg_setup_info* info) override {
         if (!flags_set) return fail(HG_ERR_INVALID, "hg_setup: hg_set_flags has not been called");
         CU(cudaEventRecord(ev0, stream));
@@ -208,6 +364,8 @@ struct Solver : SolverBase {
         dim3 pg((pitch + 255) / 256, rows);
         domain_check_kernel<<<pg, 256, 0, stream>>>(d_flags, rows, cols, pitch, op == HG_OP_BILAPLACIAN, d_counts);
         diag_kernel<T><<<pg, 256, 0, stream>>>(grid(), op == HG_OP_BILAPLACIAN, d_dinv);
+        if (use_mg()) HGTRY(build_hierarchy());
+        else free_hierarchy();
         unsigned long long counts[4];
         CU(cudaMemcpyAsync(counts, d_counts, sizeof counts, cudaMemcpyDeviceToHost, stream));
         CU(cudaEventRecord(ev1, stream));
@@ -216,7 +374,7 @@ struct Solver : SolverBase {
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, ev0, ev1));
         if (info) {
-            info->levels = 1;
+            info->levels = 1 + (int)coarse.size();
             info->empty_rows = (int)counts[0];
             info->unreferenced = (int)counts[1];
             info->n_hard = (long long)counts[2];
@@ -295,26 +453,47 @@ struct Solver : SolverBase {
         CU(cudaMemcpyAsync(d_state, &init, sizeof init, cudaMemcpyHostToDevice, stream));
         CU(cudaEventRecord(ev0, stream));
         int* done = &d_state->done;
-
-        // r = b - F(x0);  bb = r.r;  z = dinv r;  rz = r.z;  p = z
-        launch_op<1, 0>(d_x, d_b, d_r, nullptr, nullptr);
-        cg_norms_jacobi_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(plane, K, d_r, d_dinv, d_part0, d_part1);
-        cg_beta_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, d_part1, nb_vec, K, 1);
-        cg_pupdate_jacobi_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_p, d_r, d_dinv);
-        launches += 3;
-
+        CU(cudaMemsetAsync(d_p, 0, (size_t)plane * K * sizeof(T), stream));
         CgState host;
         int it = 0;
-        const int batch = 32;
+        const bool mg = use_mg();
+        if (!mg) {
+            // r = b - F(x0);  bb = r.r;  z = dinv r;  rz = r.z;  p = z
+            launch_op<1, 0>(d_x, d_b, d_r, nullptr, nullptr);
+            cg_norms_jacobi_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(plane, K, d_r, d_dinv, d_part0, d_part1);
+            cg_beta_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, d_part1, nb_vec, K, 1);
+            cg_pupdate_jacobi_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_p, d_r, d_dinv);
+            launches += 3;
+        } else {
+            // r = b - F(x0);  bb = r.r;  z = V(r);  rz = r.z;  p = z
+            launch_op<1, 2>(d_x, d_b, d_r, d_part0, nullptr);
+            cg_check_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_op, K, 1);
+            vcycle(d_z, d_r, done);
+            cg_dot_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_r, d_z, d_part1);
+            cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, d_part1, nb_vec, K, 1);
+            cg_pupdate_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_p, d_z);
+            launches += 4;
+        }
+        const int batch = mg ? 4 : 32;
         while (true) {
             const int n = std::min(batch, maxiter - it);
             for (int s = 0; s < n; ++s) {
                 launch_op<0, 1>(d_p, nullptr, d_q, d_part0, done);
                 cg_alpha_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_op, K);
-                cg_update_jacobi_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_x, d_r, d_p, d_q, d_dinv, d_part0, d_part1);
-                cg_beta_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, d_part1, nb_vec, K, 0);
-                cg_pupdate_jacobi_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_p, d_r, d_dinv);
-                launches += 4;
+                if (!mg) {
+                    cg_update_jacobi_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_x, d_r, d_p, d_q, d_dinv, d_part0, d_part1);
+                    cg_beta_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, d_part1, nb_vec, K, 0);
+                    cg_pupdate_jacobi_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_p, d_r, d_dinv);
+                    launches += 4;
+                } else {
+                    cg_update_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_x, d_r, d_p, d_q, d_part0);
+                    cg_check_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_vec, K, 0);
+                    vcycle(d_z, d_r, done);
+                    cg_dot_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_r, d_z, d_part1);
+                    cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, d_part1, nb_vec, K, 0);
+                    cg_pupdate_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_p, d_z);
+                    launches += 6;
+                }
             }
             it += n;
             CU(cudaMemcpyAsync(&host, d_state, sizeof host, cudaMemcpyDeviceToHost, stream));
@@ -342,7 +521,7 @@ struct Solver : SolverBase {
         }
         int status = HG_OK;
         if (host.done == 2 || relres != relres) status = HG_ERR_BREAKDOWN;
-        else if (host.done == 0) status = HG_ERR_NOT_CONVERGED;
+        else if (host.done != 1) status = HG_ERR_NOT_CONVERGED;   // maxiter or stagnation
         if (st) {
             st->iterations = host.iter;
             st->status = status;
@@ -467,6 +646,9 @@ int hg_upload_values(hg_handle h, const hg_values* v, hg_stats* st) { CHECK_H(h)
 int hg_solve_device(hg_handle h, double rtol, int maxiter, hg_stats* st) { CHECK_H(h); return h->impl->solve_device(rtol, maxiter, st); }
 int hg_download(hg_handle h, double* x, hg_stats* st) { CHECK_H(h); return h->impl->download(x, st); }
 int hg_bench_apply(hg_handle h, int iters, double* ms) { CHECK_H(h); return h->impl->bench_apply(iters, ms); }
+int hg_precond_apply(hg_handle h, const double* r, double* z) { CHECK_H(h); return h->impl->precond_apply(r, z); }
+int hg_mg_levels(hg_handle h) { CHECK_H(h); return h->impl->mg_levels(); }
+int hg_mg_get_level(hg_handle h, int level, int* rows, int* cols, double* coef9) { CHECK_H(h); return h->impl->mg_get_level(level, rows, cols, coef9); }
 
 int hg_solve(hg_handle h, const hg_values* vals, double* x_out, double rtol, int maxiter, hg_stats* stats) {
     CHECK_H(h);

@@ -19,10 +19,23 @@ struct CgState {
     double alpha[HG_MAXK];
     double beta[HG_MAXK];
     double tol2;            // rtol^2
+    double best;            // smallest max_k rr/bb seen so far (stagnation detection)
+    int best_iter;
     int iter;
-    int done;               // 1 converged, 2 breakdown
+    int done;               // 1 converged, 2 breakdown, 3 stagnated
     int maxiter;
 };
+
+// Stagnation: no new best residual for as long as it took to reach the best one plus 500
+// iterations.  CG residuals are not monotone, so the window is deliberately generous.
+__device__ __forceinline__ void track_stagnation(CgState* st, double worst_ratio) {
+    if (st->iter == 0 || worst_ratio < 0.99 * st->best) {
+        st->best = worst_ratio;
+        st->best_iter = st->iter;
+    } else if (st->iter - st->best_iter > 500 + st->best_iter && st->done == 0) {
+        st->done = 3;
+    }
+}
 
 // Adds `n` partial sums per channel in a fixed order (one block).
 __device__ __forceinline__ double ordered_sum(const double* part, int n, double* red) {
@@ -57,7 +70,8 @@ __global__ void cg_beta_kernel(CgState* st, const double* __restrict__ part_rr, 
     if (st->done) return;
     __shared__ double red[32];
     __shared__ int all_conv;
-    if (threadIdx.x == 0) all_conv = 1;
+    __shared__ double worst;
+    if (threadIdx.x == 0) { all_conv = 1; worst = 0.0; }
     __syncthreads();
     for (int k = 0; k < K; ++k) {
         const double rr = ordered_sum(part_rr + (long long)k * nblk, nblk, red);
@@ -73,12 +87,14 @@ __global__ void cg_beta_kernel(CgState* st, const double* __restrict__ part_rr, 
             st->rz[k] = rz;
             if (!(rr == rr) || !(rz == rz)) st->done = 2;
             if (rr > st->tol2 * st->bb[k]) all_conv = 0;
+            if (st->bb[k] > 0.0) worst = fmax(worst, rr / st->bb[k]);
         }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         if (!init) st->iter += 1;
         if (all_conv && st->done == 0) st->done = 1;
+        track_stagnation(st, worst);
     }
 }
 
@@ -170,6 +186,149 @@ cg_pupdate_jacobi_kernel(const CgState* __restrict__ st, long long plane, int K,
             st4(pk + o, pv);
         }
     }
+}
+
+// ---- generic (any preconditioner) CG kernels ----------------------------------------------------
+// convergence check right after the x / r update, so that the preconditioner launches that follow
+// turn into no-ops once the tolerance is met
+__global__ void cg_check_kernel(CgState* st, const double* __restrict__ part_rr, int nblk, int K, int init) {
+    if (st->done) return;
+    __shared__ double red[32];
+    __shared__ int all_conv;
+    __shared__ double worst;
+    if (threadIdx.x == 0) { all_conv = 1; worst = 0.0; }
+    __syncthreads();
+    for (int k = 0; k < K; ++k) {
+        const double rr = ordered_sum(part_rr + (long long)k * nblk, nblk, red);
+        if (threadIdx.x == 0) {
+            if (init) st->bb[k] = rr;
+            st->rr[k] = rr;
+            if (!(rr == rr)) st->done = 2;
+            if (rr > st->tol2 * st->bb[k]) all_conv = 0;
+            if (st->bb[k] > 0.0) worst = fmax(worst, rr / st->bb[k]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (!init) st->iter += 1;
+        if (all_conv && st->done == 0) st->done = 1;
+        track_stagnation(st, worst);
+    }
+}
+
+// after z = M^-1 r:  rz_new -> beta
+__global__ void cg_beta_rz_kernel(CgState* st, const double* __restrict__ part_rz, int nblk, int K, int init) {
+    if (st->done) return;
+    __shared__ double red[32];
+    for (int k = 0; k < K; ++k) {
+        const double rz = ordered_sum(part_rz + (long long)k * nblk, nblk, red);
+        if (threadIdx.x == 0) {
+            st->beta[k] = (!init && st->rz[k] != 0.0) ? rz / st->rz[k] : 0.0;
+            st->rz[k] = rz;
+            if (!(rz == rz) || rz < 0.0) st->done = 2;   // the preconditioner must be positive definite
+        }
+        __syncthreads();
+    }
+}
+
+// x += alpha p ; r -= alpha q ; partial sums of r.r
+template <typename T>
+__global__ void __launch_bounds__(VEC_THREADS)
+cg_update_kernel(const CgState* __restrict__ st, long long plane, int K, T* __restrict__ x, T* __restrict__ r,
+                 const T* __restrict__ p, const T* __restrict__ q, double* __restrict__ part_rr) {
+    if (st->done) return;
+    __shared__ double red[32];
+    const long long n4 = plane >> 2;
+    for (int k = 0; k < K; ++k) {
+        const T a = (T)st->alpha[k];
+        T* xk = x + k * plane; T* rk = r + k * plane;
+        const T* pk = p + k * plane; const T* qk = q + k * plane;
+        double srr = 0.0;
+        for (long long v = (long long)blockIdx.x * VEC_THREADS + threadIdx.x; v < n4; v += (long long)gridDim.x * VEC_THREADS) {
+            const long long o = v << 2;
+            V4<T> xv = ld4(xk + o), rv = ld4(rk + o);
+            const V4<T> pv = ld4(pk + o), qv = ld4(qk + o);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                xv.v[c] += a * pv.v[c];
+                rv.v[c] -= a * qv.v[c];
+                srr += (double)rv.v[c] * (double)rv.v[c];
+            }
+            st4(xk + o, xv);
+            st4(rk + o, rv);
+        }
+        const double s1 = block_sum(srr, red);
+        if (threadIdx.x == 0) part_rr[(long long)k * gridDim.x + blockIdx.x] = s1;
+    }
+}
+
+// partial sums of a.b  (a == b gives the squared norm)
+template <typename T>
+__global__ void __launch_bounds__(VEC_THREADS)
+cg_dot_kernel(const CgState* __restrict__ st, long long plane, int K, const T* __restrict__ a, const T* __restrict__ b,
+              double* __restrict__ part) {
+    if (st && st->done) return;
+    __shared__ double red[32];
+    const long long n4 = plane >> 2;
+    for (int k = 0; k < K; ++k) {
+        const T* ak = a + k * plane; const T* bk = b + k * plane;
+        double s = 0.0;
+        for (long long v = (long long)blockIdx.x * VEC_THREADS + threadIdx.x; v < n4; v += (long long)gridDim.x * VEC_THREADS) {
+            const long long o = v << 2;
+            const V4<T> av = ld4(ak + o), bv = ld4(bk + o);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s += (double)av.v[c] * (double)bv.v[c];
+        }
+        const double s1 = block_sum(s, red);
+        if (threadIdx.x == 0) part[(long long)k * gridDim.x + blockIdx.x] = s1;
+    }
+}
+
+// p = z + beta p
+template <typename T>
+__global__ void __launch_bounds__(VEC_THREADS)
+cg_pupdate_kernel(const CgState* __restrict__ st, long long plane, int K, T* __restrict__ p, const T* __restrict__ z) {
+    if (st->done) return;
+    const long long n4 = plane >> 2;
+    for (int k = 0; k < K; ++k) {
+        const T bt = (T)st->beta[k];
+        T* pk = p + k * plane; const T* zk = z + k * plane;
+        for (long long v = (long long)blockIdx.x * VEC_THREADS + threadIdx.x; v < n4; v += (long long)gridDim.x * VEC_THREADS) {
+            const long long o = v << 2;
+            V4<T> pv = ld4(pk + o);
+            const V4<T> zv = ld4(zk + o);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) pv.v[c] = zv.v[c] + bt * pv.v[c];
+            st4(pk + o, pv);
+        }
+    }
+}
+
+// z = dinv r   (Jacobi preconditioner as a stand-alone operator)
+template <typename T>
+__global__ void __launch_bounds__(VEC_THREADS)
+jacobi_apply_kernel(long long plane, int K, T* __restrict__ z, const T* __restrict__ r, const T* __restrict__ dinv) {
+    const long long n4 = plane >> 2;
+    for (int k = 0; k < K; ++k)
+        for (long long v = (long long)blockIdx.x * VEC_THREADS + threadIdx.x; v < n4; v += (long long)gridDim.x * VEC_THREADS) {
+            const long long o = v << 2;
+            const V4<T> rv = ld4(r + k * plane + o), dv = ld4(dinv + o);
+            V4<T> zv;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) zv.v[c] = dv.v[c] * rv.v[c];
+            st4(z + k * plane + o, zv);
+        }
+}
+
+// v = 0 at hard pixels and in the padding
+template <typename T>
+__global__ void mask_hard_kernel(Grid<T> g, T* __restrict__ v) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= g.pitch) return;
+    const long long o = (long long)i * g.pitch + j;
+    if (j >= g.cols || (g.flags[o] & HG_FLAG_HARD))
+        for (int k = 0; k < g.K; ++k) v[k * g.plane + o] = T(0);
 }
 
 // ---- host <-> device value conversion ---------------------------------------------------

@@ -130,6 +130,15 @@ int hg_upload_values(hg_handle h, const hg_values* vals, hg_stats* stats);
 int hg_solve_device(hg_handle h, double rtol, int maxiter, hg_stats* stats);
 int hg_download(hg_handle h, double* x_out, hg_stats* stats);
 
+/* z = M^-1 r: one application of the preconditioner (Jacobi or one multigrid V-cycle) to a
+ * host array; r is masked to the free pixels first.  For tests of symmetry / definiteness. */
+int hg_precond_apply(hg_handle h, const double* r, double* z);
+/* Multigrid hierarchy introspection: number of levels (level 0 = the flag-encoded operator),
+ * and the explicit 9-point Galerkin stencil of level >= 1 as (rows, cols, 9) float64,
+ * entry c = (di+1)*3 + (dj+1).  coef9 may be NULL to query the size only. */
+int hg_mg_levels(hg_handle h);
+int hg_mg_get_level(hg_handle h, int level, int* rows, int* cols, double* coef9);
+
 /* Times `iters` launches of the stencil kernel on device-resident data (CUDA events on
  * the solver's stream); returns mean milliseconds per launch. */
 int hg_bench_apply(hg_handle h, int iters, double* ms_per_launch);

@@ -1,0 +1,126 @@
+"""GPU: the multigrid preconditioner -- Galerkin coarse stencils against scipy's P^T A P,
+symmetry / definiteness of the V-cycle, MG-PCG against the oracle, iteration counts."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import mg_reference as mr
+from conftest import rel_err
+from harmonic_interpolation_b200 import recovery as R
+from harmonic_interpolation_b200 import solver as S
+from oracle import grid_oracle as go
+
+pytestmark = pytest.mark.gpu
+
+
+def problem(rng, rows, cols, K=1, cuts=True, soft=True, hard_p=0.04):
+    p = go.GridProblem(rows, cols, K, False)
+    p.hard = rng.random((rows, cols)) < hard_p
+    p.hard[0, 0] = True
+    p.hard_vals = rng.random((rows, cols, K))
+    if soft:
+        sm = (rng.random((rows, cols)) < 0.08) & ~p.hard
+        p.soft_w = np.where(sm, rng.uniform(0.1, 50.0, (rows, cols)), 0.0)
+        p.soft_vals = rng.random((rows, cols, K))
+    if cuts:
+        block = np.kron(rng.random((rows // 8 + 1, cols // 8 + 1)) < 0.3, np.ones((8, 8), bool))[:rows, :cols]
+        p.cut_down, p.cut_right = R.cut_planes_from_mask(block)
+    return p
+
+
+def solver_for(p, prec, precond="multigrid"):
+    s = S.GridSolver(p.rows, p.cols, p.K, False, prec, precond)
+    s.set_pattern(S.encode_flags(p.rows, p.cols, hard=p.hard, soft=p.soft_w > 0, cut_down=p.cut_down, cut_right=p.cut_right,
+                                 pen_down=p.pen_down, pen_right=p.pen_right), p.soft_w if (p.soft_w > 0).any() else None, 0.0, p.w_g)
+    return s
+
+
+@pytest.mark.parametrize("shape", [(33, 40), (64, 64), (37, 130), (100, 19)])
+def test_galerkin_stencils_match_scipy(shape):
+    rows, cols = shape
+    rng = np.random.default_rng(rows + cols)
+    p = problem(rng, rows, cols)
+    s = solver_for(p, "fp64")
+    assert s.mg_levels() >= 2
+    A, _ = go.full_system(p)
+    free = ~p.hard.ravel()
+    D = sp.diags(free.astype(float))
+    A = (D @ A @ D).tocsr()
+    active = ~p.hard
+    r, c = rows, cols
+    for level in range(1, s.mg_levels()):
+        P, cr, cc = mr.bilinear_P(r, c, active)
+        A = (P.T @ A @ P).tocsr()
+        want = mr.stencil_from_matrix(A, cr, cc)
+        got = s.mg_level_stencil(level)
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() < 1e-12 * max(1.0, np.abs(want).max()), level
+        # the Galerkin operator has no entries outside the 3x3 neighbourhood
+        assert abs(abs(A).sum() - np.abs(want).sum()) < 1e-9 * abs(A).sum()
+        active = want[:, :, 4] != 0
+        r, c = cr, cc
+    s.close()
+
+
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+def test_vcycle_is_symmetric_positive_definite(prec):
+    rng = np.random.default_rng(3)
+    p = problem(rng, 70, 90, K=2)
+    s = solver_for(p, prec)
+    a = rng.normal(size=(70, 90, 2)); b = rng.normal(size=(70, 90, 2))
+    a[p.hard] = 0; b[p.hard] = 0
+    Ma, Mb = s.precond_apply(a), s.precond_apply(b)
+    assert (Ma[p.hard] == 0).all()
+    for k in range(2):
+        ab, ba = (Mb[:, :, k] * a[:, :, k]).sum(), (Ma[:, :, k] * b[:, :, k]).sum()
+        assert abs(ab - ba) < (1e-11 if prec == "fp64" else 2e-4) * (abs(ab) + abs(ba) + 1e-30)
+        assert (Ma[:, :, k] * a[:, :, k]).sum() > 0
+    s.close()
+
+
+@pytest.mark.parametrize("shape", [(60, 52), (128, 128), (299, 200), (17, 300), (1, 500), (500, 1)])
+def test_mg_pcg_matches_oracle(shape):
+    rows, cols = shape
+    rng = np.random.default_rng(rows * 7 + cols)
+    p = problem(rng, rows, cols, K=2, cuts=min(rows, cols) > 8)
+    ref = go.solve_problem(p)
+    s = solver_for(p, "fp64")
+    out = s.solve(p.hard_vals, p.soft_vals, rtol=1e-13)
+    assert rel_err(out, ref) < 1e-9
+    it_mg = s.last_stats["iterations"]
+    s.close()
+    sj = solver_for(p, "fp64", "jacobi")
+    sj.solve(p.hard_vals, p.soft_vals, rtol=1e-13, maxiter=100000)
+    it_j = sj.last_stats["iterations"]
+    sj.close()
+    if min(rows, cols) >= 60:
+        assert it_mg * 3 < it_j, (it_mg, it_j)
+    s = solver_for(p, "fp32")
+    out = s.solve(p.hard_vals, p.soft_vals, rtol=1e-7)
+    assert rel_err(out, ref) < 1e-5
+    s.close()
+
+
+@pytest.mark.parametrize("case", ["tiles64", "disk", "pin", "iid"])
+def test_mg_iteration_counts(case):
+    """PCG iterations to 1e-6 on the mask families of the headline config (512^2): the numpy
+    prototype (tools/mg_proto.py) needs 6-7; allow 12."""
+    n = 512
+    rng = np.random.default_rng(0)
+    if case == "tiles64":
+        hard = np.kron(rng.random((n // 64, n // 64)) < 0.5, np.ones((64, 64), bool)); hard[0, 0] = True
+    elif case == "disk":
+        ii, jj = np.indices((n, n)); hard = (ii - n / 2) ** 2 + (jj - n / 2) ** 2 > n * n / (2 * np.pi)
+    elif case == "pin":
+        hard = np.zeros((n, n), bool); hard[0, 0] = True
+    else:
+        hard = rng.random((n, n)) < 0.5
+    vals = rng.random((n, n, 1))
+    for prec in ("fp32", "fp64"):
+        s = S.GridSolver(n, n, 1, False, prec, "multigrid")
+        s.set_pattern(S.encode_flags(n, n, hard=hard))
+        s.solve(hard_vals=vals, rtol=1e-6)
+        st = s.last_stats
+        assert st["iterations"] <= 12, (case, prec, st)
+        assert st["relres"] < 3e-6
+        s.close()
