@@ -1,0 +1,266 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the grid-diffusion solve path (BASELINE.json).
+
+One "step" = one complete harmonic fill of the workload (config C3 of SURVEY 8(d)): a
+16384^2 RGB image, 50 % of the pixels unknown (64x64-pixel tiles, Bernoulli(0.5), seed 0,
+pixel (0,0) opaque), solved to 1e-6 relative residual of the reduced free-pixel system.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+  value   M unknowns/s with the inputs resident in HBM (device-timed solve, CUDA events)
+  e2e     the same through the public array API with HOST buffers (H2D + solve + D2H)
+  roofline  the 5-point stencil kernel against the measured HBM copy bandwidth
+  cpu_baseline  the CPU restatement of the reference (oracle/grid_oracle.py) on a bounded sample
+
+With N > 1 (torchrun, one rank per GPU) every rank fills its own grid (independent images,
+no data-path collective; row-slab decomposition of ONE grid is the next multi-GPU step);
+value is the whole-job aggregate over the max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "harmonic_fill_throughput_at_1e-6_rel_residual"
+UNIT = "Munknowns/s"
+CPU_SAMPLE_N = 2048       # cpu_baseline leg of the default arm: one fill of this size
+REF_STEP_N = 1024         # --impl reference: each step is one fill of this size
+
+
+def workload(n, seed=0, tile=64):
+    """C3 generator: uint8 RGB image in [0,1] as float64, keep-mask in `tile`-pixel tiles."""
+    rng = np.random.default_rng(seed)
+    keep = np.kron(rng.random((n // tile, n // tile)) < 0.5, np.ones((tile, tile), bool))
+    keep[0, 0] = True
+    img8 = rng.integers(0, 256, size=(n, n, 3), dtype=np.uint8)
+    return img8, keep
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_fill(n):
+    """One fill of an n x n sample of the workload with the CPU restatement of the reference."""
+    from oracle import grid_oracle as go
+    img8, keep = workload(n)
+    img = img8 / 255.0
+    t = time.perf_counter()
+    go.fill_alpha_harmonic(img, keep)
+    dt = time.perf_counter() - t
+    return float((~keep).sum()) * 3, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    n = REF_STEP_N
+    for _ in range(args.warmup):
+        cpu_fill(n)
+    times = []
+    unknowns = 0.0
+    for _ in range(args.steps):
+        unknowns, dt = cpu_fill(n)
+        times.append(dt)
+    T = sum(times)
+    v = unknowns * args.steps / T / 1e6
+    sample = "harmonic fill of a %dx%d K=3 sample of the workload per step (vectorised scipy.sparse assembly + SuperLU)" % (n, n)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * T / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C3 harmonic alpha-fill, RGB, 50% unknown in 64x64 tiles (CPU arm: %dx%d sample)" % (n, n)},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=int(os.environ.get("HGRID_BENCH_SIZE", 16384)))
+    ap.add_argument("--rtol", type=float, default=1e-6)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from harmonic_interpolation_b200 import solver as S
+
+    n, K = args.size, 3
+    img8, keep = workload(n, seed=rank)
+    img = img8 / 255.0                       # float64 (n, n, 3), what fill_alpha_harmonic receives
+    free_px = float((~keep).sum())
+    unknowns = free_px * K
+
+    s = S.GridSolver(n, n, K, False, args.precision, "multigrid")
+    t0 = time.perf_counter()
+    info = s.set_pattern(S.encode_flags(n, n, hard=keep))
+    setup_s = time.perf_counter() - t0
+    s.upload(hard_vals=img)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident solve; every step restarts from the zero guess ----------------
+    for _ in range(args.warmup):
+        s.reset_guess()
+        st = s.solve_device(args.rtol, 500)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    dev_ms, launches, iters, relres = [], 0, 0, 0.0
+    for _ in range(args.steps):
+        s.reset_guess()
+        st = s.solve_device(args.rtol, 500)
+        dev_ms.append(st["solve_ms"])
+        launches += st["launches"] + 1
+        iters = st["iterations"]
+        relres = st["relres"]
+    barrier()
+    clocks = sampler.stop()
+    t_dev = torch.tensor([sum(dev_ms)], dtype=torch.float64, device="cuda")
+    tot_unknowns = torch.tensor([unknowns], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot_unknowns, op=dist.ReduceOp.SUM)
+    ms_per_step = float(t_dev.item()) / args.steps
+    value = float(tot_unknowns.item()) / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e: host arrays in, host array out, through the public array API --------------------
+    e2e_t = []
+    out = None
+    for i in range(1 + min(args.steps, 3)):
+        barrier()
+        t = time.perf_counter()
+        out = s.solve(hard_vals=img, rtol=args.rtol, maxiter=500)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t
+        if i > 0:
+            e2e_t.append(dt)
+    t_e2e = torch.tensor([float(np.mean(e2e_t))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = float(tot_unknowns.item()) / float(t_e2e.item()) / 1e6
+    assert (out[keep] == img[keep]).all()
+
+    # ---- roofline of the stencil kernel (CUDA events on the solver's stream) -------------------
+    W = 4 if args.precision == "fp32" else 8
+    ms_apply = s.bench_apply(20)
+    alg_bytes = float(n) * n * (K * 2 * W + 1)
+    peak, peak_src = peaks()
+    achieved = alg_bytes / (ms_apply * 1e-3) / 1e9
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.precision == "fp32" else "f64", "data": "synthetic",
+        "config": {"workload": "C3 harmonic alpha-fill %dx%d RGB, 50%% unknown in 64x64 tiles, rtol %g" % (n, n, args.rtol),
+                   "parallelism": "one grid per GPU" if world > 1 else "single GPU",
+                   "l2": "working set (%.1f GB) exceeds the 126 MB L2" % (alg_bytes / 1e9),
+                   "solver": "MG-PCG, %d levels, %s storage, fp64 reductions and refinement" % (info.levels, args.precision),
+                   "iterations": iters, "relres_true": relres, "setup_s": setup_s,
+                   "time_to_solution_ms": ms_per_step, "free_pixels": free_px},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(img.nbytes), "d2h_bytes_per_step": int(out.nbytes),
+                "seconds_per_step": float(t_e2e.item()), "api": "GridSolver.solve(hard_vals=float64 (rows, cols, 3))"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "lap_apply_kernel<%s>" % ("float" if W == 4 else "double"),
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_apply, "peak_source": peak_src,
+                     "frac_of_8TBs_nominal": achieved / 8000.0},
+    }
+    if not args.no_cpu_baseline:
+        u, dt = cpu_fill(CPU_SAMPLE_N)
+        line["cpu_baseline"] = {"value": u / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "one %dx%d K=3 fill of the same generator, %.1f s (scipy.sparse assembly + SuperLU, 1 thread; host has %d logical cores)" % (
+                                    CPU_SAMPLE_N, CPU_SAMPLE_N, dt, os.cpu_count())}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

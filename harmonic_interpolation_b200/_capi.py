@@ -56,6 +56,7 @@ SYMBOLS = {
     "hg_upload_values": (ctypes.c_int, [_H, ctypes.POINTER(Values), ctypes.POINTER(Stats)]),
     "hg_solve_device": (ctypes.c_int, [_H, ctypes.c_double, ctypes.c_int, ctypes.POINTER(Stats)]),
     "hg_download": (ctypes.c_int, [_H, _dp, ctypes.POINTER(Stats)]),
+    "hg_reset_guess": (ctypes.c_int, [_H]),
     "hg_bench_apply": (ctypes.c_int, [_H, ctypes.c_int, _dp]),
     "hg_precond_apply": (ctypes.c_int, [_H, _dp, _dp]),
     "hg_mg_levels": (ctypes.c_int, [_H]),

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -54,6 +55,7 @@ struct SolverBase {
     virtual int mg_levels() = 0;
     virtual int mg_get_level(int level, int* rows, int* cols, double* coef9) = 0;
     virtual int precond_apply(const double* r, double* z) = 0;
+    virtual int reset_guess() = 0;
 };
 
 template <typename T>
@@ -80,6 +82,11 @@ struct Solver : SolverBase {
     unsigned long long* d_counts = nullptr;
     long long launches = 0;
 
+    // fp32 mode keeps the iterate and the right-hand side in fp64 ("master") for iterative
+    // refinement; in fp64 mode these alias d_x / d_b
+    double *d_xm = nullptr, *d_bm = nullptr;
+    static constexpr bool kRefine = !std::is_same<T, double>::value;
+
     // multigrid hierarchy (levels >= 1; level 0 is the flag-encoded operator)
     T* d_z = nullptr;
     std::vector<Coarse<T>> coarse;
@@ -97,6 +104,7 @@ struct Solver : SolverBase {
         cudaFree(d_out); cudaFree(d_part0); cudaFree(d_part1); cudaFree(d_state); cudaFree(d_counts);
         free_hierarchy();
         cudaFree(d_z);
+        if (kRefine) { cudaFree(d_xm); cudaFree(d_bm); }
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -200,7 +208,14 @@ struct Solver : SolverBase {
                 CU(cudaMemsetAsync(*p, 0, bytes, stream));
             }
         if (!d_dinv) CU(cudaMalloc(&d_dinv, plane * sizeof(T)));
-        const int need = std::max(op_blocks(), vec_blocks()) * K;
+        if (kRefine) {
+            if (!d_xm) CU(cudaMalloc(&d_xm, (size_t)plane * K * sizeof(double)));
+            if (!d_bm) CU(cudaMalloc(&d_bm, (size_t)plane * K * sizeof(double)));
+        } else {
+            d_xm = reinterpret_cast<double*>(d_x);
+            d_bm = reinterpret_cast<double*>(d_b);
+        }
+        const int need = std::max(std::max(op_blocks(), vec_blocks()), ((pitch + 255) / 256) * rows) * K;
         if (need > part_cap) {
             cudaFree(d_part0); cudaFree(d_part1);
             d_part0 = d_part1 = nullptr;
@@ -258,7 +273,7 @@ struct Solver : SolverBase {
             CU(cudaMalloc(&d_dense, (size_t)n * 2 * n * sizeof(double)));
             dense_from_stencil_kernel<T><<<64, 256, 0, stream>>>(L, d_dense);
             dense_fill_kernel<T><<<(n + 127) / 128, 128, 0, stream>>>(L, d_dense);
-            gauss_jordan_kernel<<<1, 1024, n * sizeof(double), stream>>>(d_dense, n);
+            gauss_jordan_kernel<<<1, 1024, 2 * n * sizeof(double), stream>>>(d_dense, n);
         }
         CU(cudaGetLastError());
         return HG_OK;
@@ -344,10 +359,10 @@ struct Solver : SolverBase {
         mask_hard_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_r);
         if (use_mg()) {
             vcycle(d_z, d_r, nullptr);
-            export_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_z, d_out);
+            export_kernel<T, T><<<pg, 256, 0, stream>>>(grid(), d_z, d_out);
         } else {
             jacobi_apply_kernel<T><<<vec_blocks(), VEC_THREADS, 0, stream>>>(plane, K, d_q, d_r, d_dinv);
-            export_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_q, d_out);
+            export_kernel<T, T><<<pg, 256, 0, stream>>>(grid(), d_q, d_out);
         }
         CU(cudaMemcpyAsync(z, d_out, bytes, cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
@@ -410,7 +425,7 @@ struct Solver : SolverBase {
         dim3 pg((pitch + 255) / 256, rows);
         import_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_stage[0], d_p);
         launch_op<0, 0>(d_p, nullptr, d_q, nullptr, nullptr);
-        export_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_q, d_out);
+        export_kernel<T, T><<<pg, 256, 0, stream>>>(grid(), d_q, d_out);
         CU(cudaMemcpyAsync(y, d_out, bytes, cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
         CU(cudaGetLastError());
@@ -427,9 +442,9 @@ struct Solver : SolverBase {
         const double* host[5] = {v->hard_vals, v->soft_vals, v->d_down, v->d_right, v->x0};
         for (int s = 0; s < 5; ++s) HGTRY(stage(s, host[s]));
         dim3 pg((pitch + 255) / 256, rows);
-        build_problem_kernel<T><<<pg, 256, 0, stream>>>(grid(), host[0] ? d_stage[0] : nullptr, host[1] ? d_stage[1] : nullptr,
-                                                       host[2] ? d_stage[2] : nullptr, host[3] ? d_stage[3] : nullptr,
-                                                       host[4] ? d_stage[4] : nullptr, d_x, d_b);
+        build_problem_kernel<T, double><<<pg, 256, 0, stream>>>(grid(), host[0] ? d_stage[0] : nullptr, host[1] ? d_stage[1] : nullptr,
+                                                               host[2] ? d_stage[2] : nullptr, host[3] ? d_stage[3] : nullptr,
+                                                               host[4] ? d_stage[4] : nullptr, d_xm, d_bm);
         CU(cudaEventRecord(ev1, stream));
         CU(cudaStreamSynchronize(stream));
         CU(cudaGetLastError());
@@ -440,12 +455,34 @@ struct Solver : SolverBase {
         return HG_OK;
     }
 
-    // One PCG solve on device-resident x (hard values + initial guess) and b.
+    // z = M^-1 r
+    void apply_precond(T* z, const T* r, const int* done) {
+        if (use_mg()) {
+            vcycle(z, r, done);
+        } else {
+            jacobi_apply_kernel<T><<<vec_blocks(), VEC_THREADS, 0, stream>>>(plane, K, z, r, d_dinv);
+            ++launches;
+        }
+    }
+
+    // Solve on the device-resident master iterate (hard values + initial guess) and b.
+    //
+    // Outer loop (iterative refinement / verified restart): the TRUE residual r = b - F(x) is
+    // evaluated in the master precision (fp64 even in fp32 mode) and decides convergence; the
+    // inner loop is preconditioned CG on A e = r in the storage precision.  In fp64 mode the
+    // inner CG updates x in place and the outer loop only verifies (normally one pass).
     int solve_device(double rtol, int maxiter, hg_stats* st) override {
         if (!is_setup || !have_values) return fail(HG_ERR_INVALID, "hg_solve_device: values have not been uploaded");
         if (maxiter <= 0) maxiter = 100000;
         launches = 0;
         const int nb_op = op_blocks(), nb_vec = vec_blocks();
+        const dim3 pg((pitch + 255) / 256, rows);
+        const int nb_res = pg.x * pg.y;
+        const size_t vbytes = (size_t)plane * K * sizeof(T);
+        if (!d_z) {
+            CU(cudaMalloc(&d_z, vbytes));
+            CU(cudaMemsetAsync(d_z, 0, vbytes, stream));
+        }
         CgState init;
         memset(&init, 0, sizeof init);
         init.tol2 = rtol * rtol;
@@ -453,75 +490,77 @@ struct Solver : SolverBase {
         CU(cudaMemcpyAsync(d_state, &init, sizeof init, cudaMemcpyHostToDevice, stream));
         CU(cudaEventRecord(ev0, stream));
         int* done = &d_state->done;
-        CU(cudaMemsetAsync(d_p, 0, (size_t)plane * K * sizeof(T), stream));
-        CgState host;
-        int it = 0;
         const bool mg = use_mg();
-        if (!mg) {
-            // r = b - F(x0);  bb = r.r;  z = dinv r;  rz = r.z;  p = z
-            launch_op<1, 0>(d_x, d_b, d_r, nullptr, nullptr);
-            cg_norms_jacobi_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(plane, K, d_r, d_dinv, d_part0, d_part1);
-            cg_beta_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, d_part1, nb_vec, K, 1);
-            cg_pupdate_jacobi_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_p, d_r, d_dinv);
-            launches += 3;
-        } else {
-            // r = b - F(x0);  bb = r.r;  z = V(r);  rz = r.z;  p = z
-            launch_op<1, 2>(d_x, d_b, d_r, d_part0, nullptr);
-            cg_check_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_op, K, 1);
-            vcycle(d_z, d_r, done);
+        // what one inner CG run may promise: fp32 storage reduces a residual by ~1e-5 at best
+        const double inner_red = kRefine ? 1e-5 : 0.0;
+        const int max_outer = kRefine ? 8 : 4;
+        T* e = kRefine ? d_x : reinterpret_cast<T*>(d_xm);   // the vector the inner CG updates
+
+        CgState host;
+        memset(&host, 0, sizeof host);
+        double prev_ratio = 0.0;
+        int outer = 0;
+        for (;; ++outer) {
+            // true residual in master precision -> d_r (storage type), ||r||^2 -> state
+            if (kRefine) {
+                resid_master_kernel<T><<<pg, 256, 0, stream>>>(grid(), op == HG_OP_BILAPLACIAN, d_xm, d_bm, d_r, d_part0);
+                cg_outer_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_res, K, outer == 0, inner_red * inner_red);
+                ++launches;
+            } else {
+                launch_op<1, 2>(e, d_b, d_r, d_part0, nullptr);
+                cg_outer_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_op, K, outer == 0, inner_red * inner_red);
+            }
+            ++launches;
+            CU(cudaMemcpyAsync(&host, d_state, sizeof host, cudaMemcpyDeviceToHost, stream));
+            CU(cudaStreamSynchronize(stream));
+            if (host.done) break;                                   // converged (1), NaN (2) or out of iterations (4)
+            if (outer >= max_outer) break;
+            // a refinement step that did not gain a factor 4 has hit the attainable accuracy
+            if (outer > 0 && !(host.outer_ratio < 0.0625 * prev_ratio)) break;
+            prev_ratio = host.outer_ratio;
+
+            // inner PCG on A e = r, e0 = 0 (fp32 mode) or continuing from x (fp64 mode)
+            if (kRefine) CU(cudaMemsetAsync(d_x, 0, vbytes, stream));
+            apply_precond(d_z, d_r, done);
             cg_dot_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_r, d_z, d_part1);
             cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, d_part1, nb_vec, K, 1);
-            cg_pupdate_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_p, d_z);
-            launches += 4;
-        }
-        const int batch = mg ? 4 : 32;
-        while (true) {
-            const int n = std::min(batch, maxiter - it);
-            for (int s = 0; s < n; ++s) {
-                launch_op<0, 1>(d_p, nullptr, d_q, d_part0, done);
-                cg_alpha_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_op, K);
-                if (!mg) {
-                    cg_update_jacobi_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_x, d_r, d_p, d_q, d_dinv, d_part0, d_part1);
-                    cg_beta_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, d_part1, nb_vec, K, 0);
-                    cg_pupdate_jacobi_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_p, d_r, d_dinv);
-                    launches += 4;
-                } else {
-                    cg_update_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_x, d_r, d_p, d_q, d_part0);
-                    cg_check_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_vec, K, 0);
-                    vcycle(d_z, d_r, done);
+            CU(cudaMemcpyAsync(d_p, d_z, vbytes, cudaMemcpyDeviceToDevice, stream));
+            launches += 3;
+            const int batch = mg ? 4 : 32;
+            while (true) {
+                for (int s = 0; s < batch; ++s) {
+                    launch_op<0, 1>(d_p, nullptr, d_q, d_part0, done);
+                    cg_alpha_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_op, K);
+                    cg_update_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, e, d_r, d_p, d_q, d_part0);
+                    cg_check_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_vec, K);
+                    apply_precond(d_z, d_r, done);
                     cg_dot_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_r, d_z, d_part1);
                     cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, d_part1, nb_vec, K, 0);
                     cg_pupdate_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_p, d_z);
-                    launches += 6;
+                    launches += 7;
                 }
+                CU(cudaMemcpyAsync(&host, d_state, sizeof host, cudaMemcpyDeviceToHost, stream));
+                CU(cudaStreamSynchronize(stream));
+                if (host.done) break;
             }
-            it += n;
-            CU(cudaMemcpyAsync(&host, d_state, sizeof host, cudaMemcpyDeviceToHost, stream));
-            CU(cudaStreamSynchronize(stream));
-            if (host.done || it >= maxiter) break;
+            if (kRefine) {
+                axpy_master_kernel<T><<<vec_blocks(), 256, 0, stream>>>(plane * K, d_xm, d_x);
+                ++launches;
+            }
+            if (host.done == 2) break;
         }
-        // true residual of the reduced system, from scratch
-        launch_op<1, 2>(d_x, d_b, d_q, d_part0, nullptr);
-        std::vector<double> part((size_t)nb_op * K);
-        CU(cudaMemcpyAsync(part.data(), d_part0, part.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
         CU(cudaEventRecord(ev1, stream));
         CU(cudaStreamSynchronize(stream));
         CU(cudaGetLastError());
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, ev0, ev1));
 
-        double relres = 0.0, relres_cg = 0.0;
-        for (int k = 0; k < K; ++k) {
-            double s = 0.0;
-            for (int i = 0; i < nb_op; ++i) s += part[(size_t)k * nb_op + i];
-            if (host.bb[k] > 0.0) {
-                relres = std::max(relres, sqrt(s / host.bb[k]));
-                relres_cg = std::max(relres_cg, sqrt(host.rr[k] / host.bb[k]));
-            }
-        }
+        double relres = sqrt(host.outer_ratio), relres_cg = 0.0;
+        for (int k = 0; k < K; ++k)
+            if (host.bb[k] > 0.0) relres_cg = std::max(relres_cg, sqrt(host.rr[k] / host.bb[k]));
         int status = HG_OK;
         if (host.done == 2 || relres != relres) status = HG_ERR_BREAKDOWN;
-        else if (host.done != 1) status = HG_ERR_NOT_CONVERGED;   // maxiter or stagnation
+        else if (!host.outer_done) status = HG_ERR_NOT_CONVERGED;   // maxiter, stagnation or attainable accuracy
         if (st) {
             st->iterations = host.iter;
             st->status = status;
@@ -531,11 +570,20 @@ struct Solver : SolverBase {
             st->launches = launches;
             const double W = sizeof(T);
             const double npx = (double)rows * cols;
-            // un-preconditioned CG iteration: K*11W + 1 bytes per pixel (+ W for the Jacobi diagonal, read twice)
-            st->bytes_moved = npx * ((double)host.iter * (K * 11.0 * W + 1.0 + 2.0 * W) + 2.0 * (K * 3.0 * W + 1.0));
+            // un-preconditioned CG iteration: K*11W + 1 bytes per pixel; the
+            // preconditioner's traffic is not credited
+            st->bytes_moved = npx * ((double)host.iter * (K * 11.0 * W + 1.0) + (outer + 1.0) * (K * 3.0 * W + 1.0));
         }
         if (status == HG_ERR_BREAKDOWN) return fail(status, "conjugate gradients broke down (NaN or non-positive curvature): singular or under-constrained system");
-        if (status == HG_ERR_NOT_CONVERGED) return fail(status, "conjugate gradients did not reach the requested tolerance within maxiter");
+        if (status == HG_ERR_NOT_CONVERGED) return fail(status, "the true residual did not reach the requested tolerance (iteration limit, stagnation, or attainable accuracy of the arithmetic)");
+        return HG_OK;
+    }
+
+    int reset_guess() override {
+        if (!is_setup || !have_values) return fail(HG_ERR_INVALID, "hg_reset_guess: values have not been uploaded");
+        dim3 pg((pitch + 255) / 256, rows);
+        reset_guess_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_xm);
+        CU(cudaGetLastError());
         return HG_OK;
     }
 
@@ -545,7 +593,7 @@ struct Solver : SolverBase {
         if (!d_out) CU(cudaMalloc(&d_out, bytes));
         CU(cudaEventRecord(ev0, stream));
         dim3 pg((pitch + 255) / 256, rows);
-        export_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_x, d_out);
+        export_kernel<T, double><<<pg, 256, 0, stream>>>(grid(), d_xm, d_out);
         CU(cudaMemcpyAsync(x, d_out, bytes, cudaMemcpyDeviceToHost, stream));
         CU(cudaEventRecord(ev1, stream));
         CU(cudaStreamSynchronize(stream));
@@ -647,6 +695,7 @@ int hg_solve_device(hg_handle h, double rtol, int maxiter, hg_stats* st) { CHECK
 int hg_download(hg_handle h, double* x, hg_stats* st) { CHECK_H(h); return h->impl->download(x, st); }
 int hg_bench_apply(hg_handle h, int iters, double* ms) { CHECK_H(h); return h->impl->bench_apply(iters, ms); }
 int hg_precond_apply(hg_handle h, const double* r, double* z) { CHECK_H(h); return h->impl->precond_apply(r, z); }
+int hg_reset_guess(hg_handle h) { CHECK_H(h); return h->impl->reset_guess(); }
 int hg_mg_levels(hg_handle h) { CHECK_H(h); return h->impl->mg_levels(); }
 int hg_mg_get_level(hg_handle h, int level, int* rows, int* cols, double* coef9) { CHECK_H(h); return h->impl->mg_get_level(level, rows, cols, coef9); }
 

@@ -340,14 +340,27 @@ __global__ void dense_fill_kernel(Coarse<T> L, double* __restrict__ M) {
             if (L.coef[4 * L.plane + (long long)qi * L.pitch + qj] > T(0)) row[qi * L.cols + qj] = (double)a;
         }
 }
-// Gauss-Jordan without pivoting (the matrix is symmetric positive definite), one block.
+// Gauss-Jordan without pivoting, one block.  The matrix is symmetric positive SEMI-definite:
+// when the masked interpolation P loses column rank (e.g. four coarse pixels that all
+// interpolate one lone free fine pixel) A_c = P^T A P is singular but the coarse right-hand
+// side P^T r is always consistent and null vectors are annihilated by P, so any solution
+// will do.  A pivot that has collapsed (<= 1e-10 of its original diagonal) marks a dependent
+// unknown: it is set to zero by clearing its row, which yields the generalised inverse on
+// the independent set.
 __global__ void __launch_bounds__(1024) gauss_jordan_kernel(double* __restrict__ M, int n) {
-    extern __shared__ double fac[];
+    extern __shared__ double fac[];   // n factors + n original diagonals
+    double* d0 = fac + n;
     const int w = 2 * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) d0[i] = M[(long long)i * w + i];
     for (int k = 0; k < n; ++k) {
         __syncthreads();
         const double piv = M[(long long)k * w + k];
+        const bool dead = !(piv > 1e-10 * d0[k]);
         __syncthreads();
+        if (dead) {
+            for (int j = threadIdx.x; j < w; j += blockDim.x) M[(long long)k * w + j] = 0.0;
+            continue;
+        }
         for (int j = threadIdx.x; j < w; j += blockDim.x) M[(long long)k * w + j] /= piv;
         for (int i = threadIdx.x; i < n; i += blockDim.x) fac[i] = (i == k) ? 0.0 : M[(long long)i * w + k];
         __syncthreads();

@@ -18,21 +18,25 @@ struct CgState {
     double bb[HG_MAXK];     // ||b_f - A_fc x_c||^2, the reference norm of the stopping rule
     double alpha[HG_MAXK];
     double beta[HG_MAXK];
-    double tol2;            // rtol^2
+    double tol2;            // rtol^2: the stopping rule on the TRUE residual (outer check)
+    double tol2_eff;        // stopping rule of the current inner CG run (recurrence residual)
+    double outer_ratio;     // max_k rr/bb of the true residual at the last outer check
+    int outer_done;         // 1: the true residual meets rtol
+    int pad0;
     double best;            // smallest max_k rr/bb seen so far (stagnation detection)
     int best_iter;
     int iter;
-    int done;               // 1 converged, 2 breakdown, 3 stagnated
+    int done;               // inner run: 1 converged, 2 breakdown, 3 stagnated, 4 maxiter
     int maxiter;
 };
 
 // Stagnation: no new best residual for as long as it took to reach the best one plus 500
 // iterations.  CG residuals are not monotone, so the window is deliberately generous.
 __device__ __forceinline__ void track_stagnation(CgState* st, double worst_ratio) {
-    if (st->iter == 0 || worst_ratio < 0.99 * st->best) {
+    if (worst_ratio < 0.99 * st->best) {
         st->best = worst_ratio;
         st->best_iter = st->iter;
-    } else if (st->iter - st->best_iter > 500 + st->best_iter && st->done == 0) {
+    } else if (st->iter - st->best_iter > 500 + st->best_iter / 2 && st->done == 0) {
         st->done = 3;
     }
 }
@@ -63,10 +67,12 @@ __global__ void cg_alpha_kernel(CgState* st, const double* __restrict__ part_pq,
     }
 }
 
-// after the x / r update: rr, rz_new -> beta, convergence test, iteration count.
-// part_rr / part_rz hold nblk partial sums per channel.
-__global__ void cg_beta_kernel(CgState* st, const double* __restrict__ part_rr, const double* __restrict__ part_rz,
-                               int nblk, int K, int init) {
+#define VEC_THREADS 256
+
+// ---- generic (any preconditioner) CG kernels ----------------------------------------------------
+// convergence check right after the x / r update, so that the preconditioner launches that follow
+// turn into no-ops once the tolerance is met
+__global__ void cg_check_kernel(CgState* st, const double* __restrict__ part_rr, int nblk, int K) {
     if (st->done) return;
     __shared__ double red[32];
     __shared__ int all_conv;
@@ -75,124 +81,27 @@ __global__ void cg_beta_kernel(CgState* st, const double* __restrict__ part_rr, 
     __syncthreads();
     for (int k = 0; k < K; ++k) {
         const double rr = ordered_sum(part_rr + (long long)k * nblk, nblk, red);
-        const double rz = ordered_sum(part_rz + (long long)k * nblk, nblk, red);
         if (threadIdx.x == 0) {
-            if (init) {
-                st->bb[k] = rr;
-                st->beta[k] = 0.0;
-            } else {
-                st->beta[k] = st->rz[k] != 0.0 ? rz / st->rz[k] : 0.0;
-            }
             st->rr[k] = rr;
-            st->rz[k] = rz;
-            if (!(rr == rr) || !(rz == rz)) st->done = 2;
-            if (rr > st->tol2 * st->bb[k]) all_conv = 0;
+            if (!(rr == rr)) st->done = 2;
+            if (rr > st->tol2_eff * st->bb[k]) all_conv = 0;
             if (st->bb[k] > 0.0) worst = fmax(worst, rr / st->bb[k]);
         }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        if (!init) st->iter += 1;
+        st->iter += 1;
         if (all_conv && st->done == 0) st->done = 1;
+        if (st->iter >= st->maxiter && st->done == 0) st->done = 4;
         track_stagnation(st, worst);
     }
 }
 
-#define VEC_THREADS 256
-
-// x += alpha p ; r -= alpha q ; partial sums of r.r and of r.(dinv r)   (Jacobi: z = dinv r)
-template <typename T>
-__global__ void __launch_bounds__(VEC_THREADS)
-cg_update_jacobi_kernel(const CgState* __restrict__ st, long long plane, int K, T* __restrict__ x, T* __restrict__ r,
-                        const T* __restrict__ p, const T* __restrict__ q, const T* __restrict__ dinv,
-                        double* __restrict__ part_rr, double* __restrict__ part_rz) {
-    if (st->done) return;
-    __shared__ double red[32];
-    const long long n4 = plane >> 2;
-    for (int k = 0; k < K; ++k) {
-        const T a = (T)st->alpha[k];
-        T* xk = x + k * plane; T* rk = r + k * plane;
-        const T* pk = p + k * plane; const T* qk = q + k * plane;
-        double srr = 0.0, srz = 0.0;
-        for (long long v = (long long)blockIdx.x * VEC_THREADS + threadIdx.x; v < n4; v += (long long)gridDim.x * VEC_THREADS) {
-            const long long o = v << 2;
-            V4<T> xv = ld4(xk + o), rv = ld4(rk + o);
-            const V4<T> pv = ld4(pk + o), qv = ld4(qk + o), dv = ld4(dinv + o);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                xv.v[c] += a * pv.v[c];
-                rv.v[c] -= a * qv.v[c];
-                const double rd = (double)rv.v[c];
-                srr += rd * rd;
-                srz += rd * rd * (double)dv.v[c];
-            }
-            st4(xk + o, xv);
-            st4(rk + o, rv);
-        }
-        const double s1 = block_sum(srr, red);
-        const double s2 = block_sum(srz, red);
-        if (threadIdx.x == 0) {
-            part_rr[(long long)k * gridDim.x + blockIdx.x] = s1;
-            part_rz[(long long)k * gridDim.x + blockIdx.x] = s2;
-        }
-    }
-}
-
-// partial sums of r.r and r.(dinv r) without an update (initial residual)
-template <typename T>
-__global__ void __launch_bounds__(VEC_THREADS)
-cg_norms_jacobi_kernel(long long plane, int K, const T* __restrict__ r, const T* __restrict__ dinv,
-                       double* __restrict__ part_rr, double* __restrict__ part_rz) {
-    __shared__ double red[32];
-    const long long n4 = plane >> 2;
-    for (int k = 0; k < K; ++k) {
-        const T* rk = r + k * plane;
-        double srr = 0.0, srz = 0.0;
-        for (long long v = (long long)blockIdx.x * VEC_THREADS + threadIdx.x; v < n4; v += (long long)gridDim.x * VEC_THREADS) {
-            const long long o = v << 2;
-            const V4<T> rv = ld4(rk + o), dv = ld4(dinv + o);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const double rd = (double)rv.v[c];
-                srr += rd * rd;
-                srz += rd * rd * (double)dv.v[c];
-            }
-        }
-        const double s1 = block_sum(srr, red);
-        const double s2 = block_sum(srz, red);
-        if (threadIdx.x == 0) {
-            part_rr[(long long)k * gridDim.x + blockIdx.x] = s1;
-            part_rz[(long long)k * gridDim.x + blockIdx.x] = s2;
-        }
-    }
-}
-
-// p = dinv r + beta p     (Jacobi)
-template <typename T>
-__global__ void __launch_bounds__(VEC_THREADS)
-cg_pupdate_jacobi_kernel(const CgState* __restrict__ st, long long plane, int K, T* __restrict__ p,
-                         const T* __restrict__ r, const T* __restrict__ dinv) {
-    if (st->done) return;
-    const long long n4 = plane >> 2;
-    for (int k = 0; k < K; ++k) {
-        const T bt = (T)st->beta[k];
-        T* pk = p + k * plane; const T* rk = r + k * plane;
-        for (long long v = (long long)blockIdx.x * VEC_THREADS + threadIdx.x; v < n4; v += (long long)gridDim.x * VEC_THREADS) {
-            const long long o = v << 2;
-            V4<T> pv = ld4(pk + o);
-            const V4<T> rv = ld4(rk + o), dv = ld4(dinv + o);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) pv.v[c] = dv.v[c] * rv.v[c] + bt * pv.v[c];
-            st4(pk + o, pv);
-        }
-    }
-}
-
-// ---- generic (any preconditioner) CG kernels ----------------------------------------------------
-// convergence check right after the x / r update, so that the preconditioner launches that follow
-// turn into no-ops once the tolerance is met
-__global__ void cg_check_kernel(CgState* st, const double* __restrict__ part_rr, int nblk, int K, int init) {
-    if (st->done) return;
+// Outer check on the TRUE residual r = b - A x (computed in the master precision): fixes the
+// reference norm bb at the first call, decides final convergence, and arms the next inner CG
+// run, which only has to reduce the residual by `inner_red` (fp32 storage cannot do better).
+__global__ void cg_outer_kernel(CgState* st, const double* __restrict__ part_rr, int nblk, int K, int first,
+                                double inner_red2) {
     __shared__ double red[32];
     __shared__ int all_conv;
     __shared__ double worst;
@@ -201,8 +110,9 @@ __global__ void cg_check_kernel(CgState* st, const double* __restrict__ part_rr,
     for (int k = 0; k < K; ++k) {
         const double rr = ordered_sum(part_rr + (long long)k * nblk, nblk, red);
         if (threadIdx.x == 0) {
-            if (init) st->bb[k] = rr;
+            if (first) st->bb[k] = rr;
             st->rr[k] = rr;
+            st->rz[k] = 0.0;
             if (!(rr == rr)) st->done = 2;
             if (rr > st->tol2 * st->bb[k]) all_conv = 0;
             if (st->bb[k] > 0.0) worst = fmax(worst, rr / st->bb[k]);
@@ -210,9 +120,14 @@ __global__ void cg_check_kernel(CgState* st, const double* __restrict__ part_rr,
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        if (!init) st->iter += 1;
-        if (all_conv && st->done == 0) st->done = 1;
-        track_stagnation(st, worst);
+        st->outer_ratio = worst;
+        if (st->done != 2) {
+            st->outer_done = all_conv;
+            st->done = all_conv ? 1 : (st->iter >= st->maxiter ? 4 : 0);
+            st->tol2_eff = fmax(0.25 * st->tol2, inner_red2 * worst);
+            st->best = worst;
+            st->best_iter = st->iter;
+        }
     }
 }
 
@@ -331,31 +246,42 @@ __global__ void mask_hard_kernel(Grid<T> g, T* __restrict__ v) {
         for (int k = 0; k < g.K; ++k) v[k * g.plane + o] = T(0);
 }
 
+// x = 0 at free pixels (hard values stay): restart from the zero guess
+template <typename T>
+__global__ void reset_guess_kernel(Grid<T> g, double* __restrict__ x) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= g.cols) return;
+    const long long o = (long long)i * g.pitch + j;
+    if (!(g.flags[o] & HG_FLAG_HARD))
+        for (int k = 0; k < g.K; ++k) x[k * g.plane + o] = 0.0;
+}
+
 // ---- host <-> device value conversion ---------------------------------------------------
 // Host arrays are (rows, cols, K) float64 with K innermost; device planes are K planes of
 // pitch-strided T.  build_problem_kernel forms, in one pass over the staged host arrays,
 //   x   = hard value at hard pixels, x0 (or 0) at free pixels
 //   b   = s_p v_p + w_g [ d_down(up) - d_down(p) + d_right(left) - d_right(p) ]  at free pixels
 // (C^T W Crhs of recovery.py:927, 1321; +w d at the far endpoint, -w d at (i,j)).
-template <typename T>
+template <typename T, typename TO>
 __global__ void build_problem_kernel(Grid<T> g, const double* __restrict__ hard_vals, const double* __restrict__ soft_vals,
                                      const double* __restrict__ d_down, const double* __restrict__ d_right,
-                                     const double* __restrict__ x0, T* __restrict__ x, T* __restrict__ b) {
+                                     const double* __restrict__ x0, TO* __restrict__ x, TO* __restrict__ b) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
     if (j >= g.pitch) return;
     const long long o = (long long)i * g.pitch + j;
     const int K = g.K;
     if (j >= g.cols) {
-        for (int k = 0; k < K; ++k) { x[k * g.plane + o] = T(0); b[k * g.plane + o] = T(0); }
+        for (int k = 0; k < K; ++k) { x[k * g.plane + o] = TO(0); b[k * g.plane + o] = TO(0); }
         return;
     }
     const long long h = ((long long)i * g.cols + j) * K;  // host offset
     const unsigned f = g.flags[o];
     if (f & HG_FLAG_HARD) {
         for (int k = 0; k < K; ++k) {
-            x[k * g.plane + o] = hard_vals ? (T)hard_vals[h + k] : T(0);
-            b[k * g.plane + o] = T(0);
+            x[k * g.plane + o] = hard_vals ? (TO)hard_vals[h + k] : TO(0);
+            b[k * g.plane + o] = TO(0);
         }
         return;
     }
@@ -374,14 +300,14 @@ __global__ void build_problem_kernel(Grid<T> g, const double* __restrict__ hard_
         if (pr) v -= wg * d_right[h + k];
         if (pu) v += wg * d_down[h - (long long)g.cols * K + k];
         if (pl) v += wg * d_right[h - K + k];
-        b[k * g.plane + o] = (T)v;
-        x[k * g.plane + o] = x0 ? (T)x0[h + k] : T(0);
+        b[k * g.plane + o] = (TO)v;
+        x[k * g.plane + o] = x0 ? (TO)x0[h + k] : TO(0);
     }
 }
 
-// planar T -> (rows, cols, K) float64
-template <typename T>
-__global__ void export_kernel(Grid<T> g, const T* __restrict__ x, double* __restrict__ out) {
+// planar -> (rows, cols, K) float64
+template <typename T, typename TI>
+__global__ void export_kernel(Grid<T> g, const TI* __restrict__ x, double* __restrict__ out) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
     if (j >= g.cols) return;

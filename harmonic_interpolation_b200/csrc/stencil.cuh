@@ -292,4 +292,82 @@ __global__ void domain_check_kernel(const uint8_t* __restrict__ fl, int rows, in
     }
 }
 
+
+// --------------------------------------------------------------------------------------
+// Master-precision residual for the fp32 mode (iterative refinement): x and b are kept in
+// fp64, r = b - F(x) is evaluated in fp64 and rounded to the storage type T only at the end.
+// Runs once per outer refinement step (2-4 times per solve), so it is a plain
+// one-thread-per-pixel kernel.  Also leaves per-block partial sums of r.r.
+// --------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ double u_master(const Grid<T>& g, const double* x, int i, int j) {
+    // (L_refl x)_(i,j); 0 outside the grid
+    if (i < 0 || i >= g.rows || j < 0 || j >= g.cols) return 0.0;
+    const long long o = (long long)i * g.pitch + j;
+    double u = 0.0;
+    if (axis_v(g.flags, g.rows, g.cols, g.pitch, i, j)) u += 2.0 * x[o] - x[o - g.pitch] - x[o + g.pitch];
+    if (axis_h(g.flags, g.rows, g.cols, g.pitch, i, j)) u += 2.0 * x[o] - x[o - 1] - x[o + 1];
+    return 0.25 * u;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+resid_master_kernel(Grid<T> g, int bilap, const double* __restrict__ x, const double* __restrict__ b,
+                    T* __restrict__ r, double* __restrict__ partial) {
+    __shared__ double red[32];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    const int nblk = gridDim.x * gridDim.y;
+    const int blin = blockIdx.y * gridDim.x + blockIdx.x;
+    const bool inside = j < g.pitch;
+    const long long o = (long long)i * g.pitch + j;
+    bool free_px = false;
+    unsigned f = 0, fu = 0, fl = 0;
+    if (inside && j < g.cols) {
+        f = g.flags[o];
+        free_px = !(f & HG_FLAG_HARD);
+        fu = i > 0 ? g.flags[o - g.pitch] : 0u;
+        fl = j > 0 ? g.flags[o - 1] : 0u;
+    }
+    for (int k = 0; k < g.K; ++k) {
+        const double* xk = x + k * g.plane;
+        double res = 0.0;
+        if (free_px) {
+            const double xc = xk[o];
+            double v = (double)soft_w(g, o, f) * xc;
+            if (!bilap) {
+                if (i > 0) v += (double)w_down(g, i - 1, j, fu) * (xc - xk[o - g.pitch]);
+                if (i + 1 < g.rows) v += (double)w_down(g, i, j, f) * (xc - xk[o + g.pitch]);
+                if (j > 0) v += (double)w_right(g, i, j - 1, fl) * (xc - xk[o - 1]);
+                if (j + 1 < g.cols) v += (double)w_right(g, i, j, f) * (xc - xk[o + 1]);
+            } else {
+                const int av = axis_v(g.flags, g.rows, g.cols, g.pitch, i, j), ah = axis_h(g.flags, g.rows, g.cols, g.pitch, i, j);
+                double t = 0.0;
+                if (av || ah) t += 2.0 * (av + ah) * u_master(g, xk, i, j);
+                if (axis_v(g.flags, g.rows, g.cols, g.pitch, i - 1, j)) t -= u_master(g, xk, i - 1, j);
+                if (axis_v(g.flags, g.rows, g.cols, g.pitch, i + 1, j)) t -= u_master(g, xk, i + 1, j);
+                if (axis_h(g.flags, g.rows, g.cols, g.pitch, i, j - 1)) t -= u_master(g, xk, i, j - 1);
+                if (axis_h(g.flags, g.rows, g.cols, g.pitch, i, j + 1)) t -= u_master(g, xk, i, j + 1);
+                v += 0.25 * t;
+                if (i > 0) v += (double)pen_down(g, i - 1, fu) * (xc - xk[o - g.pitch]);
+                if (i + 1 < g.rows) v += (double)pen_down(g, i, f) * (xc - xk[o + g.pitch]);
+                if (j > 0) v += (double)pen_right(g, j - 1, fl) * (xc - xk[o - 1]);
+                if (j + 1 < g.cols) v += (double)pen_right(g, j, f) * (xc - xk[o + 1]);
+            }
+            res = b[k * g.plane + o] - v;
+        }
+        if (inside) r[k * g.plane + o] = (T)res;
+        const double s = block_sum(res * res, red);
+        if (threadIdx.x == 0) partial[(long long)k * nblk + blin] = s;
+    }
+}
+
+// x (fp64 master) += e (storage type); hard pixels and padding have e == 0
+template <typename T>
+__global__ void __launch_bounds__(256)
+axpy_master_kernel(long long n, double* __restrict__ x, const T* __restrict__ e) {
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (long long)gridDim.x * blockDim.x)
+        x[v] += (double)e[v];
+}
+
 }  // namespace hg

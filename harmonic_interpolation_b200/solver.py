@@ -26,7 +26,7 @@ def default_rtol(precision):
     v = os.environ.get("HGRID_RTOL")
     if v is not None:
         return float(v)
-    return 1e-13 if precision == "fp64" else 1e-7
+    return 1e-13 if precision == "fp64" else 1e-9
 
 
 def accept_relres(precision):
@@ -35,7 +35,7 @@ def accept_relres(precision):
     v = os.environ.get("HGRID_ACCEPT_RELRES")
     if v is not None:
         return float(v)
-    return 1e-10 if precision == "fp64" else 1e-5
+    return 1e-10 if precision == "fp64" else 1e-7
 
 
 def encode_flags(rows, cols, hard=None, soft=None, cut_down=None, cut_right=None, pen_down=None, pen_right=None):
@@ -156,6 +156,9 @@ class GridSolver:
         if code not in (C.OK, C.ERR_NOT_CONVERGED):
             C.check(code)
         return self.last_stats
+
+    def reset_guess(self):
+        C.check(self._lib.hg_reset_guess(self._h))
 
     def download(self):
         out = np.empty((self.rows, self.cols, self.K), np.float64)

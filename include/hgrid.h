@@ -129,6 +129,9 @@ int hg_solve(hg_handle h, const hg_values* vals, double* x_out, double rtol, int
 int hg_upload_values(hg_handle h, const hg_values* vals, hg_stats* stats);
 int hg_solve_device(hg_handle h, double rtol, int maxiter, hg_stats* stats);
 int hg_download(hg_handle h, double* x_out, hg_stats* stats);
+/* Sets the device-resident iterate back to the zero guess on the free pixels (hard values
+ * stay), so that hg_solve_device can be timed repeatedly on the same uploaded values. */
+int hg_reset_guess(hg_handle h);
 
 /* z = M^-1 r: one application of the preconditioner (Jacobi or one multigrid V-cycle) to a
  * host array; r is masked to the free pixels first.  For tests of symmetry / definiteness. */

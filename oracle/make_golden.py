@@ -119,7 +119,9 @@ def main():
                     out[key] = quiet(R.solve_grid_linear, rows, cols, dx, dy, v, bil, False, cu, w)
     # value constraints only (no gradients): plain Dirichlet problem
     out["g_out_lap_valuesonly"] = quiet(R.solve_grid_linear, rows, cols, None, None, vc, False, False, cuts, None)
-    out["g_out_bilap_valuesonly"] = quiet(R.solve_grid_linear, rows, cols, None, None, vc, True, False, cuts, None)
+    # (no cuts here: with the cut block each component would hold fewer than 3 pins and the
+    #  bilaplacian system would be rank deficient -- not a valid golden)
+    out["g_out_bilap_valuesonly"] = quiet(R.solve_grid_linear, rows, cols, None, None, vc, True, False, None, None)
 
     # ---- smooth_bumps / smooth_bumps2 (doctest inputs, recovery.py:1360-1365, 1437-1444) -
     g = 5 * np.outer(np.sin(np.linspace(0, np.pi, 20)), np.cos(np.linspace(0, np.pi, 24)))

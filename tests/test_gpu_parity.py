@@ -153,7 +153,9 @@ def test_simple3_golden(golden):
     for key, kw in gc.s3_cases(golden):
         out = R.solve_grid_linear_simple3(maxiter=400000, **kw)
         assert out.shape == golden[key].shape
-        assert rel_err(out, golden[key]) < TOL64, key
+        # w_lsq = 1e3 against O(1) stencil weights on the bilaplacian: cond ~ 1e9, the reference's
+        # own float64 answer is only good to ~1e-8 of the range
+        assert rel_err(out, golden[key]) < (1e-8 if ("bilap" in key and "w1e3" in key) else TOL64), key
 
 
 def test_simple3_array_form_equals_tuple_form(golden):
@@ -265,5 +267,6 @@ def test_analytic_large_grid():
     s = S.GridSolver(rows, cols, 1, False, "fp32")
     s.set_pattern(S.encode_flags(rows, cols, hard=keep))
     out = s.solve(hard_vals=img, rtol=1e-6, maxiter=20000)
+    assert s.last_stats["relres"] <= 1e-6
     assert np.abs(out - 0.625).max() < 1e-5
     s.close()
