@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "fine.cuh"
 #include "mg.cuh"
 #include "pcg.cuh"
 #include "stencil.cuh"
@@ -91,6 +92,11 @@ struct Solver : SolverBase {
     T* d_z = nullptr;
     std::vector<Coarse<T>> coarse;
     double* d_dense = nullptr;   // [A | A^-1] of the coarsest level
+    // tile path (Laplacian + multigrid): activity map and per-tile partial sums
+    uint8_t* d_tile_active = nullptr;
+    double *d_tpart0 = nullptr, *d_tpart1 = nullptr;
+    int tiles_x = 0, tiles_y = 0;
+    bool has_pen = false;
 
     Solver(int r, int c, int k, int o) : rows(r), cols(c), K(k), op(o) {
         pitch = round_up(cols, 32);
@@ -105,6 +111,7 @@ struct Solver : SolverBase {
         free_hierarchy();
         cudaFree(d_z);
         if (kRefine) { cudaFree(d_xm); cudaFree(d_bm); }
+        cudaFree(d_tile_active); cudaFree(d_tpart0); cudaFree(d_tpart1);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -116,7 +123,7 @@ struct Solver : SolverBase {
         CU(cudaEventCreate(&ev1));
         CU(cudaMalloc(&d_flags, plane));
         CU(cudaMalloc(&d_state, sizeof(CgState)));
-        CU(cudaMalloc(&d_counts, 4 * sizeof(unsigned long long)));
+        CU(cudaMalloc(&d_counts, 8 * sizeof(unsigned long long)));
         return HG_OK;
     }
 
@@ -237,8 +244,31 @@ struct Solver : SolverBase {
 
     bool use_mg() const { return precond == HG_PRECOND_MULTIGRID && op == HG_OP_LAPLACIAN; }
 
+    dim3 tile_grid() const { return dim3(tiles_x, tiles_y); }
+    int ntiles() const { return tiles_x * tiles_y; }
+
+    int build_tiles() {
+        tiles_x = (pitch + FT_X - 1) / FT_X;
+        tiles_y = (rows + FT_Y - 1) / FT_Y;
+        cudaFree(d_tile_active); cudaFree(d_tpart0); cudaFree(d_tpart1);
+        d_tile_active = nullptr; d_tpart0 = d_tpart1 = nullptr;
+        CU(cudaMalloc(&d_tile_active, ntiles()));
+        CU(cudaMalloc(&d_tpart0, (size_t)ntiles() * K * sizeof(double)));
+        CU(cudaMalloc(&d_tpart1, (size_t)ntiles() * K * sizeof(double)));
+        // inactive tiles never write their partial sums: they must read as zero
+        CU(cudaMemsetAsync(d_tpart0, 0, (size_t)ntiles() * K * sizeof(double), stream));
+        CU(cudaMemsetAsync(d_tpart1, 0, (size_t)ntiles() * K * sizeof(double), stream));
+        tile_activity_kernel<<<tile_grid(), 256, 0, stream>>>(d_flags, rows, cols, pitch, d_tile_active);
+        CU(cudaFuncSetAttribute(mg_down0_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM(T)));
+        CU(cudaFuncSetAttribute(mg_down0_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM(T)));
+        CU(cudaFuncSetAttribute(mg_up0_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM(T)));
+        CU(cudaFuncSetAttribute(mg_up0_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM(T)));
+        return HG_OK;
+    }
+
     int build_hierarchy() {
         free_hierarchy();
+        HGTRY(build_tiles());
         if (!d_z) {
             CU(cudaMalloc(&d_z, (size_t)plane * K * sizeof(T)));
             CU(cudaMemsetAsync(d_z, 0, (size_t)plane * K * sizeof(T), stream));
@@ -279,30 +309,24 @@ struct Solver : SolverBase {
         return HG_OK;
     }
 
-    // z = M^-1 r : one V(1,1) cycle from a zero initial guess
-    void vcycle(T* z, const T* r, const int* done) {
-        FineAcc<T> fa{grid()};
-        const dim3 rb((cols / 2 + 1 + 255) / 256, rows);
-        cudaMemsetAsync(z, 0, (size_t)plane * K * sizeof(T), stream);
-        rbgs0_kernel<T><<<rb, 256, 0, stream>>>(fa, z, r, 0, done);
-        rbgs0_kernel<T><<<rb, 256, 0, stream>>>(fa, z, r, 1, done);
-        launches += 3;
+    // z = M^-1 r : one V(1,1) cycle from a zero initial guess; also leaves the per-tile partial
+    // sums of r.z in part_rz.  Level 0 is two fused tile kernels (fine.cuh).
+    void vcycle(T* z, const T* r, const int* done, double* part_rz) {
+        const Grid<T> g = grid();
         const int nl = (int)coarse.size();
+        const size_t smem = FT_SMEM(T);
         if (nl > 0) {
-            {
-                const Coarse<T>& L = coarse[0];
-                dim3 g((L.pitch + 255) / 256, L.rows);
-                resid_restrict_kernel<T, FineAcc<T>><<<g, 256, 0, stream>>>(fa, z, r, L, K, done);
-                ++launches;
-            }
+            if (has_pen) mg_down0_kernel<T, true><<<tile_grid(), FT_THREADS, smem, stream>>>(g, r, coarse[0], d_tile_active, done);
+            else mg_down0_kernel<T, false><<<tile_grid(), FT_THREADS, smem, stream>>>(g, r, coarse[0], d_tile_active, done);
+            ++launches;
             for (int l = 0; l + 1 < nl; ++l) {
                 const Coarse<T>& L = coarse[l];
                 dim3 mg((L.cols / 2 + 1 + 255) / 256, (L.rows + 1) / 2);
                 for (int c = 0; c < 4; ++c) mcgs_kernel<T><<<mg, 256, 0, stream>>>(L, c, done);
                 const Coarse<T>& Lc = coarse[l + 1];
-                dim3 g((Lc.pitch + 255) / 256, Lc.rows);
+                dim3 gg((Lc.pitch + 255) / 256, Lc.rows);
                 CoarseAcc<T> ca{L};
-                resid_restrict_kernel<T, CoarseAcc<T>><<<g, 256, 0, stream>>>(ca, L.x, L.b, Lc, K, done);
+                resid_restrict_kernel<T, CoarseAcc<T>><<<gg, 256, 0, stream>>>(ca, L.x, L.b, Lc, K, done);
                 launches += 5;
             }
             {
@@ -314,19 +338,19 @@ struct Solver : SolverBase {
             for (int l = nl - 2; l >= 0; --l) {
                 const Coarse<T>& L = coarse[l];
                 CoarseAcc<T> ca{L};
-                dim3 g((L.cols + 255) / 256, L.rows);
-                prolong_add_kernel<T, CoarseAcc<T>><<<g, 256, 0, stream>>>(ca, L.x, coarse[l + 1], K, done);
+                dim3 gg((L.cols + 255) / 256, L.rows);
+                prolong_add_kernel<T, CoarseAcc<T>><<<gg, 256, 0, stream>>>(ca, L.x, coarse[l + 1], K, done);
                 dim3 mg((L.cols / 2 + 1 + 255) / 256, (L.rows + 1) / 2);
                 for (int c = 3; c >= 0; --c) mcgs_kernel<T><<<mg, 256, 0, stream>>>(L, c, done);
                 launches += 5;
             }
-            dim3 g((cols + 255) / 256, rows);
-            prolong_add_kernel<T, FineAcc<T>><<<g, 256, 0, stream>>>(fa, z, coarse[0], K, done);
-            ++launches;
         }
-        rbgs0_kernel<T><<<rb, 256, 0, stream>>>(fa, z, r, 1, done);
-        rbgs0_kernel<T><<<rb, 256, 0, stream>>>(fa, z, r, 0, done);
-        launches += 2;
+        Coarse<T> c0;
+        memset(&c0, 0, sizeof c0);
+        if (nl > 0) c0 = coarse[0];
+        if (has_pen) mg_up0_kernel<T, true><<<tile_grid(), FT_THREADS, smem, stream>>>(g, r, z, c0, nl > 0, d_tile_active, part_rz, done);
+        else mg_up0_kernel<T, false><<<tile_grid(), FT_THREADS, smem, stream>>>(g, r, z, c0, nl > 0, d_tile_active, part_rz, done);
+        ++launches;
     }
 
     int mg_levels() override { return 1 + (int)coarse.size(); }
@@ -358,7 +382,7 @@ struct Solver : SolverBase {
         import_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_stage[0], d_r);
         mask_hard_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_r);
         if (use_mg()) {
-            vcycle(d_z, d_r, nullptr);
+            vcycle(d_z, d_r, nullptr, d_tpart1);
             export_kernel<T, T><<<pg, 256, 0, stream>>>(grid(), d_z, d_out);
         } else {
             jacobi_apply_kernel<T><<<vec_blocks(), VEC_THREADS, 0, stream>>>(plane, K, d_q, d_r, d_dinv);
@@ -375,13 +399,14 @@ struct Solver : SolverBase {
         if (!flags_set) return fail(HG_ERR_INVALID, "hg_setup: hg_set_flags has not been called");
         CU(cudaEventRecord(ev0, stream));
         HGTRY(ensure_vectors());
-        CU(cudaMemsetAsync(d_counts, 0, 4 * sizeof(unsigned long long), stream));
+        CU(cudaMemsetAsync(d_counts, 0, 8 * sizeof(unsigned long long), stream));
         dim3 pg((pitch + 255) / 256, rows);
         domain_check_kernel<<<pg, 256, 0, stream>>>(d_flags, rows, cols, pitch, op == HG_OP_BILAPLACIAN, d_counts);
         diag_kernel<T><<<pg, 256, 0, stream>>>(grid(), op == HG_OP_BILAPLACIAN, d_dinv);
+        has_pen = w_g != 0.0;   // refined below once the flag counts are known
         if (use_mg()) HGTRY(build_hierarchy());
         else free_hierarchy();
-        unsigned long long counts[4];
+        unsigned long long counts[8];
         CU(cudaMemcpyAsync(counts, d_counts, sizeof counts, cudaMemcpyDeviceToHost, stream));
         CU(cudaEventRecord(ev1, stream));
         CU(cudaStreamSynchronize(stream));
@@ -416,6 +441,16 @@ struct Solver : SolverBase {
         return HG_OK;
     }
 
+    // y = F(x) with the kernel the solver itself uses for this configuration
+    void apply_op(const T* x, T* y) {
+        if (use_mg()) {
+            lap_tile_kernel<T, 0, 0><<<tile_grid(), FT_THREADS, 0, stream>>>(grid(), x, nullptr, y, d_tile_active, nullptr, nullptr);
+            ++launches;
+        } else {
+            launch_op<0, 0>(x, nullptr, y, nullptr, nullptr);
+        }
+    }
+
     int apply(const double* x, double* y) override {
         if (!is_setup) return fail(HG_ERR_INVALID, "hg_apply: hg_setup has not been called");
         if (!x || !y) return fail(HG_ERR_INVALID, "hg_apply: NULL buffer");
@@ -424,7 +459,8 @@ struct Solver : SolverBase {
         if (!d_out) CU(cudaMalloc(&d_out, bytes));
         dim3 pg((pitch + 255) / 256, rows);
         import_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_stage[0], d_p);
-        launch_op<0, 0>(d_p, nullptr, d_q, nullptr, nullptr);
+        CU(cudaMemsetAsync(d_q, 0, (size_t)plane * K * sizeof(T), stream));
+        apply_op(d_p, d_q);
         export_kernel<T, T><<<pg, 256, 0, stream>>>(grid(), d_q, d_out);
         CU(cudaMemcpyAsync(y, d_out, bytes, cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
@@ -455,26 +491,20 @@ struct Solver : SolverBase {
         return HG_OK;
     }
 
-    // z = M^-1 r
-    void apply_precond(T* z, const T* r, const int* done) {
-        if (use_mg()) {
-            vcycle(z, r, done);
-        } else {
-            jacobi_apply_kernel<T><<<vec_blocks(), VEC_THREADS, 0, stream>>>(plane, K, z, r, d_dinv);
-            ++launches;
-        }
-    }
-
     // Solve on the device-resident master iterate (hard values + initial guess) and b.
     //
     // Outer loop (iterative refinement / verified restart): the TRUE residual r = b - F(x) is
     // evaluated in the master precision (fp64 even in fp32 mode) and decides convergence; the
     // inner loop is preconditioned CG on A e = r in the storage precision.  In fp64 mode the
     // inner CG updates x in place and the outer loop only verifies (normally one pass).
+    //
+    // Two kernel sets: the tile path (Laplacian + multigrid, fine.cuh: fused V-cycle legs, tile
+    // skipping) and the flat path (bilaplacian, or Jacobi on request).
     int solve_device(double rtol, int maxiter, hg_stats* st) override {
         if (!is_setup || !have_values) return fail(HG_ERR_INVALID, "hg_solve_device: values have not been uploaded");
         if (maxiter <= 0) maxiter = 100000;
         launches = 0;
+        const bool mg = use_mg();
         const int nb_op = op_blocks(), nb_vec = vec_blocks();
         const dim3 pg((pitch + 255) / 256, rows);
         const int nb_res = pg.x * pg.y;
@@ -490,11 +520,16 @@ struct Solver : SolverBase {
         CU(cudaMemcpyAsync(d_state, &init, sizeof init, cudaMemcpyHostToDevice, stream));
         CU(cudaEventRecord(ev0, stream));
         int* done = &d_state->done;
-        const bool mg = use_mg();
+        const Grid<T> g = grid();
         // what one inner CG run may promise: fp32 storage reduces a residual by ~1e-5 at best
         const double inner_red = kRefine ? 1e-5 : 0.0;
         const int max_outer = kRefine ? 8 : 4;
         T* e = kRefine ? d_x : reinterpret_cast<T*>(d_xm);   // the vector the inner CG updates
+        // large grids: look at the state after every iteration (a sync costs microseconds, an
+        // iteration milliseconds); small grids: enqueue batches, the surplus launches are no-ops
+        const long long npix = (long long)rows * cols;
+        const int batch = npix >= (1LL << 22) ? 1 : (mg ? 4 : 32);
+        const int nt = mg ? ntiles() : 0;
 
         CgState host;
         memset(&host, 0, sizeof host);
@@ -503,14 +538,16 @@ struct Solver : SolverBase {
         for (;; ++outer) {
             // true residual in master precision -> d_r (storage type), ||r||^2 -> state
             if (kRefine) {
-                resid_master_kernel<T><<<pg, 256, 0, stream>>>(grid(), op == HG_OP_BILAPLACIAN, d_xm, d_bm, d_r, d_part0);
+                resid_master_kernel<T><<<pg, 256, 0, stream>>>(g, op == HG_OP_BILAPLACIAN, d_xm, d_bm, d_r, d_part0);
                 cg_outer_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_res, K, outer == 0, inner_red * inner_red);
-                ++launches;
+            } else if (mg) {
+                lap_tile_kernel<T, 1, 2><<<tile_grid(), FT_THREADS, 0, stream>>>(g, e, d_b, d_r, d_tile_active, d_tpart0, nullptr);
+                cg_outer_kernel<<<1, 1024, 0, stream>>>(d_state, d_tpart0, nt, K, outer == 0, inner_red * inner_red);
             } else {
                 launch_op<1, 2>(e, d_b, d_r, d_part0, nullptr);
                 cg_outer_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_op, K, outer == 0, inner_red * inner_red);
             }
-            ++launches;
+            launches += 2;
             CU(cudaMemcpyAsync(&host, d_state, sizeof host, cudaMemcpyDeviceToHost, stream));
             CU(cudaStreamSynchronize(stream));
             if (host.done) break;                                   // converged (1), NaN (2) or out of iterations (4)
@@ -521,23 +558,40 @@ struct Solver : SolverBase {
 
             // inner PCG on A e = r, e0 = 0 (fp32 mode) or continuing from x (fp64 mode)
             if (kRefine) CU(cudaMemsetAsync(d_x, 0, vbytes, stream));
-            apply_precond(d_z, d_r, done);
-            cg_dot_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_r, d_z, d_part1);
-            cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, d_part1, nb_vec, K, 1);
-            CU(cudaMemcpyAsync(d_p, d_z, vbytes, cudaMemcpyDeviceToDevice, stream));
-            launches += 3;
-            const int batch = mg ? 4 : 32;
+            if (mg) {
+                vcycle(d_z, d_r, done, d_tpart1);
+                cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, d_tpart1, nt, K, 1);
+                cg_pupdate_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, d_p, d_z, d_tile_active, 1);
+                launches += 2;
+            } else {
+                jacobi_apply_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(plane, K, d_z, d_r, d_dinv);
+                cg_dot_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_r, d_z, d_part1);
+                cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, d_part1, nb_vec, K, 1);
+                CU(cudaMemcpyAsync(d_p, d_z, vbytes, cudaMemcpyDeviceToDevice, stream));
+                launches += 4;
+            }
             while (true) {
                 for (int s = 0; s < batch; ++s) {
-                    launch_op<0, 1>(d_p, nullptr, d_q, d_part0, done);
-                    cg_alpha_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_op, K);
-                    cg_update_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, e, d_r, d_p, d_q, d_part0);
-                    cg_check_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_vec, K);
-                    apply_precond(d_z, d_r, done);
-                    cg_dot_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_r, d_z, d_part1);
-                    cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, d_part1, nb_vec, K, 0);
-                    cg_pupdate_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_p, d_z);
-                    launches += 7;
+                    if (mg) {
+                        lap_tile_kernel<T, 0, 1><<<tile_grid(), FT_THREADS, 0, stream>>>(g, d_p, nullptr, d_q, d_tile_active, d_tpart0, done);
+                        cg_alpha_kernel<<<1, 1024, 0, stream>>>(d_state, d_tpart0, nt, K);
+                        cg_update_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, e, d_r, d_p, d_q, d_tile_active, d_tpart0);
+                        cg_check_kernel<<<1, 1024, 0, stream>>>(d_state, d_tpart0, nt, K);
+                        vcycle(d_z, d_r, done, d_tpart1);
+                        cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, d_tpart1, nt, K, 0);
+                        cg_pupdate_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, d_p, d_z, d_tile_active, 0);
+                        launches += 6;
+                    } else {
+                        launch_op<0, 1>(d_p, nullptr, d_q, d_part0, done);
+                        cg_alpha_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_op, K);
+                        cg_update_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, e, d_r, d_p, d_q, d_part0);
+                        cg_check_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_vec, K);
+                        jacobi_apply_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(plane, K, d_z, d_r, d_dinv);
+                        cg_dot_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_r, d_z, d_part1);
+                        cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, d_part1, nb_vec, K, 0);
+                        cg_pupdate_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_p, d_z);
+                        launches += 7;
+                    }
                 }
                 CU(cudaMemcpyAsync(&host, d_state, sizeof host, cudaMemcpyDeviceToHost, stream));
                 CU(cudaStreamSynchronize(stream));
@@ -607,9 +661,9 @@ struct Solver : SolverBase {
     int bench_apply(int iters, double* ms_out) override {
         if (!is_setup) return fail(HG_ERR_INVALID, "hg_bench_apply: hg_setup has not been called");
         if (iters <= 0) iters = 1;
-        for (int w = 0; w < 3; ++w) launch_op<0, 0>(d_p, nullptr, d_q, nullptr, nullptr);
+        for (int w = 0; w < 3; ++w) apply_op(d_p, d_q);
         CU(cudaEventRecord(ev0, stream));
-        for (int s = 0; s < iters; ++s) launch_op<0, 0>(d_p, nullptr, d_q, nullptr, nullptr);
+        for (int s = 0; s < iters; ++s) apply_op(d_p, d_q);
         CU(cudaEventRecord(ev1, stream));
         CU(cudaStreamSynchronize(stream));
         CU(cudaGetLastError());
