@@ -119,9 +119,14 @@ def main():
                     out[key] = quiet(R.solve_grid_linear, rows, cols, dx, dy, v, bil, False, cu, w)
     # value constraints only (no gradients): plain Dirichlet problem
     out["g_out_lap_valuesonly"] = quiet(R.solve_grid_linear, rows, cols, None, None, vc, False, False, cuts, None)
-    # (no cuts here: with the cut block each component would hold fewer than 3 pins and the
-    #  bilaplacian system would be rank deficient -- not a valid golden)
-    out["g_out_bilap_valuesonly"] = quiet(R.solve_grid_linear, rows, cols, None, None, vc, True, False, None, None)
+    # The null space of L_refl^T L_refl is spanned by {1, i, j, i*j} (the bilinear saddle is discrete
+    # harmonic and affine along every side), per cut-off component: with the 3 pins above the
+    # bilaplacian system is singular and SuperLU's answer arbitrary -- not a valid golden.  Use 4 pins
+    # in general position and no cuts.
+    vc4 = vc + [(30, 5, 0.25)]
+    out["g_vc4_ij"] = np.asarray([(i, j) for i, j, _ in vc4], np.int32)
+    out["g_vc4_v"] = np.asarray([v for _, _, v in vc4])
+    out["g_out_bilap_valuesonly"] = quiet(R.solve_grid_linear, rows, cols, None, None, vc4, True, False, None, None)
 
     # ---- smooth_bumps / smooth_bumps2 (doctest inputs, recovery.py:1360-1365, 1437-1444) -
     g = 5 * np.outer(np.sin(np.linspace(0, np.pi, 20)), np.cos(np.linspace(0, np.pi, 24)))

@@ -48,7 +48,8 @@ def g_cases(g):
                     yield key, dict(rows=rows, cols=cols, dx_constraints=dx, dy_constraints=dy, value_constraints=v,
                                     bilaplacian=bil, cut_edges=cu, w_lsq=w)
     yield "g_out_lap_valuesonly", dict(rows=rows, cols=cols, value_constraints=vc, bilaplacian=False, cut_edges=cuts)
-    yield "g_out_bilap_valuesonly", dict(rows=rows, cols=cols, value_constraints=vc, bilaplacian=True, cut_edges=None)
+    vc4 = [(int(i), int(j), float(v)) for (i, j), v in zip(g["g_vc4_ij"], g["g_vc4_v"])]
+    yield "g_out_bilap_valuesonly", dict(rows=rows, cols=cols, value_constraints=vc4, bilaplacian=True, cut_edges=None)
 
 
 def sb_cases(g):
