@@ -96,10 +96,10 @@ struct Solver : SolverBase {
     uint8_t* d_tile_active = nullptr;
     double *d_tpart0 = nullptr, *d_tpart1 = nullptr;
     int tiles_x = 0, tiles_y = 0;
-    // region tilings of the two fused V-cycle legs (interior 58x26 / 60x28) and their activity
-    uint8_t *d_down_active = nullptr, *d_up_active = nullptr;
-    double* d_upart = nullptr;
-    double* d_lpart = nullptr;   // partial sums of the stencil kernel (two blocks per tile)
+    uint8_t* d_down_active = nullptr;   // tiles with a free pixel within one pixel (restriction reaches that far)
+    uint8_t* d_code = nullptr;          // one byte of edge-weight codes per pixel (fine.cuh)
+    double* d_lpart = nullptr;          // partial sums of the stencil kernel (two blocks per tile)
+    bool b_is_zero = false;             // no soft / gradient constraints: the right-hand side is identically 0
     bool has_pen = false;
 
     Solver(int r, int c, int k, int o) : rows(r), cols(c), K(k), op(o) {
@@ -116,7 +116,7 @@ struct Solver : SolverBase {
         cudaFree(d_z);
         if (kRefine) { cudaFree(d_xm); cudaFree(d_bm); }
         cudaFree(d_tile_active); cudaFree(d_tpart0); cudaFree(d_tpart1);
-        cudaFree(d_down_active); cudaFree(d_up_active); cudaFree(d_upart); cudaFree(d_lpart);
+        cudaFree(d_down_active); cudaFree(d_code); cudaFree(d_lpart);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -250,9 +250,7 @@ struct Solver : SolverBase {
     bool use_mg() const { return precond == HG_PRECOND_MULTIGRID && op == HG_OP_LAPLACIAN; }
 
     dim3 tile_grid() const { return dim3(tiles_x, tiles_y); }
-    dim3 down_grid() const { return dim3(LegTiling<DOWN_H>::tiles_x(cols), LegTiling<DOWN_H>::tiles_y(rows)); }
-    dim3 up_grid() const { return dim3(LegTiling<UP_H>::tiles_x(cols), LegTiling<UP_H>::tiles_y(rows)); }
-    int n_up() const { dim3 u = up_grid(); return u.x * u.y; }
+
     int ntiles() const { return tiles_x * tiles_y; }
 
     int build_tiles() {
@@ -266,22 +264,19 @@ struct Solver : SolverBase {
         // inactive tiles never write their partial sums: they must read as zero
         CU(cudaMemsetAsync(d_tpart0, 0, (size_t)ntiles() * K * sizeof(double), stream));
         CU(cudaMemsetAsync(d_tpart1, 0, (size_t)ntiles() * K * sizeof(double), stream));
-        tile_activity_kernel<<<tile_grid(), 256, 0, stream>>>(d_flags, rows, cols, pitch, d_tile_active);
-        cudaFree(d_down_active); cudaFree(d_up_active); cudaFree(d_upart); cudaFree(d_lpart);
-        d_down_active = d_up_active = nullptr; d_upart = d_lpart = nullptr;
+        cudaFree(d_down_active); cudaFree(d_code); cudaFree(d_lpart);
+        d_down_active = d_code = nullptr; d_lpart = nullptr;
+        CU(cudaMalloc(&d_down_active, ntiles()));
+        CU(cudaMalloc(&d_code, plane));
         CU(cudaMalloc(&d_lpart, (size_t)n_lap() * K * sizeof(double)));
         CU(cudaMemsetAsync(d_lpart, 0, (size_t)n_lap() * K * sizeof(double), stream));
-        const dim3 dg = down_grid(), ug = up_grid();
-        CU(cudaMalloc(&d_down_active, (size_t)dg.x * dg.y));
-        CU(cudaMalloc(&d_up_active, (size_t)ug.x * ug.y));
-        CU(cudaMalloc(&d_upart, (size_t)ug.x * ug.y * K * sizeof(double)));
-        CU(cudaMemsetAsync(d_upart, 0, (size_t)ug.x * ug.y * K * sizeof(double), stream));
-        region_activity_kernel<DOWN_H><<<dg, 256, 0, stream>>>(d_flags, rows, cols, pitch, d_down_active);
-        region_activity_kernel<UP_H><<<ug, 256, 0, stream>>>(d_flags, rows, cols, pitch, d_up_active);
-        CU(cudaFuncSetAttribute(mg_down0_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, false>)));
-        CU(cudaFuncSetAttribute(mg_down0_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, true>)));
-        CU(cudaFuncSetAttribute(mg_up0_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, false>)));
-        CU(cudaFuncSetAttribute(mg_up0_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, true>)));
+        tile_activity_kernel<<<tile_grid(), 256, 0, stream>>>(d_flags, rows, cols, pitch, 0, d_tile_active);
+        tile_activity_kernel<<<tile_grid(), 256, 0, stream>>>(d_flags, rows, cols, pitch, 1, d_down_active);
+        opcode_kernel<T><<<dim3((pitch + 255) / 256, rows), 256, 0, stream>>>(grid(), d_code);
+        CU(cudaFuncSetAttribute(mg_down0_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, DOWN_H, false>)));
+        CU(cudaFuncSetAttribute(mg_down0_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, DOWN_H, true>)));
+        CU(cudaFuncSetAttribute(mg_up0_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, UP_H, false>)));
+        CU(cudaFuncSetAttribute(mg_up0_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, UP_H, true>)));
         return HG_OK;
     }
 
@@ -334,8 +329,8 @@ struct Solver : SolverBase {
         const Grid<T> g = grid();
         const int nl = (int)coarse.size();
         if (nl > 0) {
-            if (has_pen) mg_down0_kernel<T, true><<<down_grid(), FT_THREADS, sizeof(RegionSmem<T, true>), stream>>>(g, r, coarse[0], d_down_active, done);
-            else mg_down0_kernel<T, false><<<down_grid(), FT_THREADS, sizeof(RegionSmem<T, false>), stream>>>(g, r, coarse[0], d_down_active, done);
+            if (has_pen) mg_down0_kernel<T, true><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, DOWN_H, true>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
+            else mg_down0_kernel<T, false><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, DOWN_H, false>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
             ++launches;
             for (int l = 0; l + 1 < nl; ++l) {
                 const Coarse<T>& L = coarse[l];
@@ -366,8 +361,8 @@ struct Solver : SolverBase {
         Coarse<T> c0;
         memset(&c0, 0, sizeof c0);
         if (nl > 0) c0 = coarse[0];
-        if (has_pen) mg_up0_kernel<T, true><<<up_grid(), FT_THREADS, sizeof(RegionSmem<T, true>), stream>>>(g, r, z, c0, nl > 0, d_up_active, part_rz, done);
-        else mg_up0_kernel<T, false><<<up_grid(), FT_THREADS, sizeof(RegionSmem<T, false>), stream>>>(g, r, z, c0, nl > 0, d_up_active, part_rz, done);
+        if (has_pen) mg_up0_kernel<T, true><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, UP_H, true>), stream>>>(g, d_code, r, z, c0, nl > 0, d_tile_active, part_rz, done);
+        else mg_up0_kernel<T, false><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, UP_H, false>), stream>>>(g, d_code, r, z, c0, nl > 0, d_tile_active, part_rz, done);
         ++launches;
     }
 
@@ -400,7 +395,7 @@ struct Solver : SolverBase {
         import_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_stage[0], d_r);
         mask_hard_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_r);
         if (use_mg()) {
-            vcycle(d_z, d_r, nullptr, d_upart);
+            vcycle(d_z, d_r, nullptr, d_tpart1);
             export_kernel<T, T><<<pg, 256, 0, stream>>>(grid(), d_z, d_out);
         } else {
             jacobi_apply_kernel<T><<<vec_blocks(), VEC_THREADS, 0, stream>>>(plane, K, d_q, d_r, d_dinv);
@@ -462,23 +457,29 @@ struct Solver : SolverBase {
     dim3 lap_grid() const { return dim3(tiles_x, (rows + LT_ROWS - 1) / LT_ROWS); }
     int n_lap() const { dim3 l = lap_grid(); return l.x * l.y; }
 
-    template <int MODE, int DOT>
-    void launch_lap_tile(const T* x, const T* b, T* y, double* partial, const int* done) {
+    template <typename TX, int MODE, int DOT, bool PEN>
+    void launch_lap_tile_kc(const TX* x, const TX* b, T* y, double* partial, const int* done) {
         const Grid<T> g = grid();
         const dim3 lg = lap_grid();
-        switch (std::min(K, 4)) {
-            case 1: lap_tile_kernel<T, MODE, DOT, 1><<<lg, FT_THREADS, 0, stream>>>(g, x, b, y, d_tile_active, partial, done); break;
-            case 2: lap_tile_kernel<T, MODE, DOT, 2><<<lg, FT_THREADS, 0, stream>>>(g, x, b, y, d_tile_active, partial, done); break;
-            case 3: lap_tile_kernel<T, MODE, DOT, 3><<<lg, FT_THREADS, 0, stream>>>(g, x, b, y, d_tile_active, partial, done); break;
-            default: lap_tile_kernel<T, MODE, DOT, 4><<<lg, FT_THREADS, 0, stream>>>(g, x, b, y, d_tile_active, partial, done); break;
+        // fp64 operands: two channels per pass keep the loads in registers without spilling
+        switch (std::min(K, sizeof(TX) == 8 ? 2 : 4)) {
+            case 1: lap_tile_kernel<T, TX, MODE, DOT, 1, PEN><<<lg, FT_THREADS, 0, stream>>>(g, d_code, x, b, y, d_tile_active, partial, done); break;
+            case 2: lap_tile_kernel<T, TX, MODE, DOT, 2, PEN><<<lg, FT_THREADS, 0, stream>>>(g, d_code, x, b, y, d_tile_active, partial, done); break;
+            case 3: lap_tile_kernel<T, TX, MODE, DOT, 3, PEN><<<lg, FT_THREADS, 0, stream>>>(g, d_code, x, b, y, d_tile_active, partial, done); break;
+            default: lap_tile_kernel<T, TX, MODE, DOT, 4, PEN><<<lg, FT_THREADS, 0, stream>>>(g, d_code, x, b, y, d_tile_active, partial, done); break;
         }
         ++launches;
+    }
+    template <typename TX, int MODE, int DOT>
+    void launch_lap_tile(const TX* x, const TX* b, T* y, double* partial, const int* done) {
+        if (has_pen) launch_lap_tile_kc<TX, MODE, DOT, true>(x, b, y, partial, done);
+        else launch_lap_tile_kc<TX, MODE, DOT, false>(x, b, y, partial, done);
     }
 
     // y = F(x) with the kernel the solver itself uses for this configuration
     void apply_op(const T* x, T* y) {
         if (use_mg()) {
-            launch_lap_tile<0, 0>(x, nullptr, y, nullptr, nullptr);
+            launch_lap_tile<T, 0, 0>(x, nullptr, y, nullptr, nullptr);
         } else {
             launch_op<0, 0>(x, nullptr, y, nullptr, nullptr);
         }
@@ -509,6 +510,7 @@ struct Solver : SolverBase {
         if (!v) v = &z;
         CU(cudaEventRecord(ev0, stream));
         const double* host[5] = {v->hard_vals, v->soft_vals, v->d_down, v->d_right, v->x0};
+        b_is_zero = !v->soft_vals && !v->d_down && !v->d_right;
         for (int s = 0; s < 5; ++s) HGTRY(stage(s, host[s]));
         dim3 pg((pitch + 255) / 256, rows);
         build_problem_kernel<T, double><<<pg, 256, 0, stream>>>(grid(), host[0] ? d_stage[0] : nullptr, host[1] ? d_stage[1] : nullptr,
@@ -570,13 +572,14 @@ struct Solver : SolverBase {
         int outer = 0;
         for (;; ++outer) {
             // true residual in master precision -> d_r (storage type), ||r||^2 -> state
-            if (kRefine) {
-                resid_master_kernel<T><<<pg, 256, 0, stream>>>(g, op == HG_OP_BILAPLACIAN, d_xm, d_bm, d_r, d_part0);
-                cg_outer_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_res, K, outer == 0, inner_red * inner_red);
-            } else if (mg) {
-                launch_lap_tile<1, 2>(e, d_b, d_r, d_lpart, nullptr);
+            if (mg) {
+                // master-precision residual with the tile kernel (x, b in fp64 even in fp32 mode)
+                launch_lap_tile<double, 1, 2>(d_xm, b_is_zero ? nullptr : d_bm, d_r, d_lpart, nullptr);
                 cg_outer_kernel<<<1, 1024, 0, stream>>>(d_state, d_lpart, n_lap(), K, outer == 0, inner_red * inner_red);
                 --launches;
+            } else if (kRefine) {
+                resid_master_kernel<T><<<pg, 256, 0, stream>>>(g, op == HG_OP_BILAPLACIAN, d_xm, d_bm, d_r, d_part0);
+                cg_outer_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_res, K, outer == 0, inner_red * inner_red);
             } else {
                 launch_op<1, 2>(e, d_b, d_r, d_part0, nullptr);
                 cg_outer_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_op, K, outer == 0, inner_red * inner_red);
@@ -593,8 +596,8 @@ struct Solver : SolverBase {
             // inner PCG on A e = r, e0 = 0 (fp32 mode) or continuing from x (fp64 mode)
             if (kRefine) CU(cudaMemsetAsync(d_x, 0, vbytes, stream));
             if (mg) {
-                vcycle(d_z, d_r, done, d_upart);
-                cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, d_upart, n_up(), K, 1);
+                vcycle(d_z, d_r, done, d_tpart1);
+                cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, d_tpart1, nt, K, 1);
                 cg_pupdate_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, d_p, d_z, d_tile_active, 1);
                 launches += 2;
             } else {
@@ -607,13 +610,13 @@ struct Solver : SolverBase {
             while (true) {
                 for (int s = 0; s < batch; ++s) {
                     if (mg) {
-                        launch_lap_tile<0, 1>(d_p, nullptr, d_q, d_lpart, done);
+                        launch_lap_tile<T, 0, 1>(d_p, nullptr, d_q, d_lpart, done);
                         cg_alpha_kernel<<<1, 1024, 0, stream>>>(d_state, d_lpart, n_lap(), K);
                         --launches;
                         cg_update_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, e, d_r, d_p, d_q, d_tile_active, d_tpart0);
                         cg_check_kernel<<<1, 1024, 0, stream>>>(d_state, d_tpart0, nt, K);
-                        vcycle(d_z, d_r, done, d_upart);
-                        cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, d_upart, n_up(), K, 0);
+                        vcycle(d_z, d_r, done, d_tpart1);
+                        cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, d_tpart1, nt, K, 0);
                         cg_pupdate_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, d_p, d_z, d_tile_active, 0);
                         launches += 6;
                     } else {
@@ -633,7 +636,8 @@ struct Solver : SolverBase {
                 if (host.done) break;
             }
             if (kRefine) {
-                axpy_master_kernel<T><<<vec_blocks(), 256, 0, stream>>>(plane * K, d_xm, d_x);
+                if (mg) axpy_master_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(g, d_xm, d_x, d_tile_active);
+                else axpy_master_kernel<T><<<vec_blocks(), 256, 0, stream>>>(plane * K, d_xm, d_x);
                 ++launches;
             }
             if (host.done == 2) break;
