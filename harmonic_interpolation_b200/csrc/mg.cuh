@@ -199,11 +199,14 @@ mcgs_kernel(Coarse<T> L, int colour, const int* __restrict__ done) {
     const int j = 2 * (blockIdx.x * blockDim.x + threadIdx.x) + (colour & 1);
     if (i >= L.rows || j >= L.cols) return;
     const long long o = (long long)i * L.pitch + j;
+    // inactive pixels (inside fully constrained areas) are decided on the centre coefficient alone,
+    // before the other eight planes are touched
+    const T c4 = L.coef[4 * L.plane + o];
+    if (!(c4 > T(0))) return;
     T cf[9];
 #pragma unroll
-    for (int c = 0; c < 9; ++c) cf[c] = L.coef[c * L.plane + o];
-    if (!(cf[4] > T(0))) return;
-    const T inv = T(1) / cf[4];
+    for (int c = 0; c < 9; ++c) cf[c] = c == 4 ? c4 : L.coef[c * L.plane + o];
+    const T inv = T(1) / c4;
     for (int k = 0; k < L.K; ++k) {
         T* xk = L.x + k * L.plane;
         T v = L.b[k * L.plane + o];
