@@ -1,5 +1,7 @@
 // hgrid.cu -- solver handle, PCG driver and the C ABI of libhgrid.so (see include/hgrid.h).
+#include <dlfcn.h>
 #include <math.h>
+#include <nccl.h>
 #include <string.h>
 
 #include <algorithm>
@@ -41,6 +43,60 @@ static int fail(int code, const std::string& msg) {
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
+// ---- NCCL, bound at run time -------------------------------------------------------------------
+// Only the multi-GPU slab mode needs NCCL; it is opened with dlopen on first use so that the
+// library has no hard dependency on it (in a torch process this resolves to the libnccl.so.2 that
+// torch has already loaded).
+struct Nccl {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+static Nccl g_nccl;
+
+static int nccl_load() {
+    if (g_nccl.ok) return HG_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return fail(HG_ERR_INVALID, std::string("multi-GPU mode needs NCCL: ") + dlerror());
+#define HG_SYM(field, name)                                                           \
+    *(void**)(&g_nccl.field) = dlsym(g_nccl.lib, name);                               \
+    if (!g_nccl.field) return fail(HG_ERR_INVALID, std::string("NCCL symbol missing: ") + name)
+    HG_SYM(GetUniqueId, "ncclGetUniqueId");
+    HG_SYM(CommInitRank, "ncclCommInitRank");
+    HG_SYM(CommDestroy, "ncclCommDestroy");
+    HG_SYM(AllReduce, "ncclAllReduce");
+    HG_SYM(Send, "ncclSend");
+    HG_SYM(Recv, "ncclRecv");
+    HG_SYM(GroupStart, "ncclGroupStart");
+    HG_SYM(GroupEnd, "ncclGroupEnd");
+    HG_SYM(GetErrorString, "ncclGetErrorString");
+#undef HG_SYM
+    g_nccl.ok = true;
+    return HG_OK;
+}
+
+#define NC(call)                                                                                   \
+    do {                                                                                           \
+        ncclResult_t r_ = (call);                                                                  \
+        if (r_ != ncclSuccess) {                                                                   \
+            char buf_[512];                                                                        \
+            snprintf(buf_, sizeof buf_, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); \
+            return fail(HG_ERR_CUDA, buf_);                                                        \
+        }                                                                                          \
+    } while (0)
+
 struct SolverBase {
     virtual ~SolverBase() {}
     virtual int set_flags(const uint8_t* f) = 0;
@@ -57,6 +113,7 @@ struct SolverBase {
     virtual int mg_get_level(int level, int* rows, int* cols, double* coef9) = 0;
     virtual int precond_apply(const double* r, double* z) = 0;
     virtual int reset_guess() = 0;
+    virtual int comm_init(const uint8_t* id, int rank, int world, int ghost_top, int ghost_bottom) = 0;
 };
 
 template <typename T>
@@ -88,6 +145,11 @@ struct Solver : SolverBase {
     double *d_xm = nullptr, *d_bm = nullptr;
     static constexpr bool kRefine = !std::is_same<T, double>::value;
 
+    // multi-GPU slab mode: this solver owns a band of rows of a larger grid; the rows directly
+    // above / below (ghost rows, flagged hard) mirror the neighbouring slabs
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1, ghost_top = 0, ghost_bottom = 0;
+
     // multigrid hierarchy (levels >= 1; level 0 is the flag-encoded operator)
     T* d_z = nullptr;
     std::vector<Coarse<T>> coarse;
@@ -117,6 +179,7 @@ struct Solver : SolverBase {
         if (kRefine) { cudaFree(d_xm); cudaFree(d_bm); }
         cudaFree(d_tile_active); cudaFree(d_tpart0); cudaFree(d_tpart1);
         cudaFree(d_down_active); cudaFree(d_code); cudaFree(d_lpart);
+        if (comm && g_nccl.ok) g_nccl.CommDestroy(comm);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -526,6 +589,78 @@ struct Solver : SolverBase {
         return HG_OK;
     }
 
+    int comm_init(const uint8_t* id, int rank_, int world_, int gt, int gb) override {
+        if (world_ < 1 || rank_ < 0 || rank_ >= world_) return fail(HG_ERR_INVALID, "hg_comm_init: bad rank / world");
+        if (op != HG_OP_LAPLACIAN) return fail(HG_ERR_INVALID, "hg_comm_init: the slab mode supports the Laplacian operator only");
+        if (gt < 0 || gt > 1 || gb < 0 || gb > 1 || (rank_ == 0 && gt) || (rank_ == world_ - 1 && gb) || gt + gb >= rows)
+            return fail(HG_ERR_INVALID, "hg_comm_init: bad ghost rows");
+        rank = rank_; world = world_; ghost_top = gt; ghost_bottom = gb;
+        if (world > 1) {
+            if (!id) return fail(HG_ERR_INVALID, "hg_comm_init: NULL id");
+            HGTRY(nccl_load());
+            ncclUniqueId uid;
+            memcpy(&uid, id, sizeof uid);
+            NC(g_nccl.CommInitRank(&comm, world, uid, rank));
+        }
+        return HG_OK;
+    }
+
+    // ghost rows of v (K planes) <- the neighbours' boundary rows
+    template <typename V>
+    int exchange(V* v) {
+        if (world <= 1) return HG_OK;
+        const ncclDataType_t dt = sizeof(V) == 8 ? ncclDouble : ncclFloat;
+        NC(g_nccl.GroupStart());
+        for (int k = 0; k < K; ++k) {
+            V* base = v + (long long)k * plane;
+            if (ghost_top) {
+                NC(g_nccl.Send(base + (long long)ghost_top * pitch, pitch, dt, rank - 1, comm, stream));
+                NC(g_nccl.Recv(base, pitch, dt, rank - 1, comm, stream));
+            }
+            if (ghost_bottom) {
+                NC(g_nccl.Send(base + (long long)(rows - 1 - ghost_bottom) * pitch, pitch, dt, rank + 1, comm, stream));
+                NC(g_nccl.Recv(base + (long long)(rows - 1) * pitch, pitch, dt, rank + 1, comm, stream));
+            }
+        }
+        NC(g_nccl.GroupEnd());
+        return HG_OK;
+    }
+
+    int allreduce_tmp() {
+        NC(g_nccl.AllReduce(d_state->tmp, d_state->tmp, K, ncclDouble, ncclSum, comm, stream));
+        return HG_OK;
+    }
+
+    // the four scalar stages; with several slabs each is split around an allreduce of the local sums
+    int stage_alpha(const double* part, int n) {
+        if (world <= 1) { cg_alpha_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, K, 0); return HG_OK; }
+        cg_alpha_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, K, 1);
+        HGTRY(allreduce_tmp());
+        cg_alpha_kernel<<<1, 32, 0, stream>>>(d_state, part, n, K, 2);
+        return HG_OK;
+    }
+    int stage_check(const double* part, int n) {
+        if (world <= 1) { cg_check_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, K, 0); return HG_OK; }
+        cg_check_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, K, 1);
+        HGTRY(allreduce_tmp());
+        cg_check_kernel<<<1, 32, 0, stream>>>(d_state, part, n, K, 2);
+        return HG_OK;
+    }
+    int stage_beta(const double* part, int n, int init) {
+        if (world <= 1) { cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, K, init, 0); return HG_OK; }
+        cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, K, init, 1);
+        HGTRY(allreduce_tmp());
+        cg_beta_rz_kernel<<<1, 32, 0, stream>>>(d_state, part, n, K, init, 2);
+        return HG_OK;
+    }
+    int stage_outer(const double* part, int n, int first, double red2) {
+        if (world <= 1) { cg_outer_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, K, first, red2, 0); return HG_OK; }
+        cg_outer_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, K, first, red2, 1);
+        HGTRY(allreduce_tmp());
+        cg_outer_kernel<<<1, 32, 0, stream>>>(d_state, part, n, K, first, red2, 2);
+        return HG_OK;
+    }
+
     // Solve on the device-resident master iterate (hard values + initial guess) and b.
     //
     // Outer loop (iterative refinement / verified restart): the TRUE residual r = b - F(x) is
@@ -574,15 +709,18 @@ struct Solver : SolverBase {
             // true residual in master precision -> d_r (storage type), ||r||^2 -> state
             if (mg) {
                 // master-precision residual with the tile kernel (x, b in fp64 even in fp32 mode)
+                HGTRY(exchange(d_xm));
                 launch_lap_tile<double, 1, 2>(d_xm, b_is_zero ? nullptr : d_bm, d_r, d_lpart, nullptr);
-                cg_outer_kernel<<<1, 1024, 0, stream>>>(d_state, d_lpart, n_lap(), K, outer == 0, inner_red * inner_red);
+                HGTRY(stage_outer(d_lpart, n_lap(), outer == 0, inner_red * inner_red));
                 --launches;
             } else if (kRefine) {
+                HGTRY(exchange(d_xm));
                 resid_master_kernel<T><<<pg, 256, 0, stream>>>(g, op == HG_OP_BILAPLACIAN, d_xm, d_bm, d_r, d_part0);
-                cg_outer_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_res, K, outer == 0, inner_red * inner_red);
+                HGTRY(stage_outer(d_part0, nb_res, outer == 0, inner_red * inner_red));
             } else {
+                HGTRY(exchange(e));
                 launch_op<1, 2>(e, d_b, d_r, d_part0, nullptr);
-                cg_outer_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_op, K, outer == 0, inner_red * inner_red);
+                HGTRY(stage_outer(d_part0, nb_op, outer == 0, inner_red * inner_red));
             }
             launches += 2;
             CU(cudaMemcpyAsync(&host, d_state, sizeof host, cudaMemcpyDeviceToHost, stream));
@@ -597,36 +735,38 @@ struct Solver : SolverBase {
             if (kRefine) CU(cudaMemsetAsync(d_x, 0, vbytes, stream));
             if (mg) {
                 vcycle(d_z, d_r, done, d_tpart1);
-                cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, d_tpart1, nt, K, 1);
+                HGTRY(stage_beta(d_tpart1, nt, 1));
                 cg_pupdate_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, d_p, d_z, d_tile_active, 1);
                 launches += 2;
             } else {
                 jacobi_apply_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(plane, K, d_z, d_r, d_dinv);
                 cg_dot_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_r, d_z, d_part1);
-                cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, d_part1, nb_vec, K, 1);
+                HGTRY(stage_beta(d_part1, nb_vec, 1));
                 CU(cudaMemcpyAsync(d_p, d_z, vbytes, cudaMemcpyDeviceToDevice, stream));
                 launches += 4;
             }
             while (true) {
                 for (int s = 0; s < batch; ++s) {
                     if (mg) {
+                        HGTRY(exchange(d_p));
                         launch_lap_tile<T, 0, 1>(d_p, nullptr, d_q, d_lpart, done);
-                        cg_alpha_kernel<<<1, 1024, 0, stream>>>(d_state, d_lpart, n_lap(), K);
+                        HGTRY(stage_alpha(d_lpart, n_lap()));
                         --launches;
                         cg_update_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, e, d_r, d_p, d_q, d_tile_active, d_tpart0);
-                        cg_check_kernel<<<1, 1024, 0, stream>>>(d_state, d_tpart0, nt, K);
+                        HGTRY(stage_check(d_tpart0, nt));
                         vcycle(d_z, d_r, done, d_tpart1);
-                        cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, d_tpart1, nt, K, 0);
+                        HGTRY(stage_beta(d_tpart1, nt, 0));
                         cg_pupdate_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, d_p, d_z, d_tile_active, 0);
                         launches += 6;
                     } else {
+                        HGTRY(exchange(d_p));
                         launch_op<0, 1>(d_p, nullptr, d_q, d_part0, done);
-                        cg_alpha_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_op, K);
+                        HGTRY(stage_alpha(d_part0, nb_op));
                         cg_update_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, e, d_r, d_p, d_q, d_part0);
-                        cg_check_kernel<<<1, 1024, 0, stream>>>(d_state, d_part0, nb_vec, K);
+                        HGTRY(stage_check(d_part0, nb_vec));
                         jacobi_apply_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(plane, K, d_z, d_r, d_dinv);
                         cg_dot_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_r, d_z, d_part1);
-                        cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, d_part1, nb_vec, K, 0);
+                        HGTRY(stage_beta(d_part1, nb_vec, 0));
                         cg_pupdate_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_p, d_z);
                         launches += 7;
                     }
@@ -788,6 +928,18 @@ int hg_solve_device(hg_handle h, double rtol, int maxiter, hg_stats* st) { CHECK
 int hg_download(hg_handle h, double* x, hg_stats* st) { CHECK_H(h); return h->impl->download(x, st); }
 int hg_bench_apply(hg_handle h, int iters, double* ms) { CHECK_H(h); return h->impl->bench_apply(iters, ms); }
 int hg_precond_apply(hg_handle h, const double* r, double* z) { CHECK_H(h); return h->impl->precond_apply(r, z); }
+int hg_comm_unique_id(uint8_t* id) {
+    if (!id) return fail(HG_ERR_INVALID, "hg_comm_unique_id: NULL id");
+    HGTRY(nccl_load());
+    ncclUniqueId uid;
+    NC(g_nccl.GetUniqueId(&uid));
+    memcpy(id, &uid, sizeof uid);
+    return HG_OK;
+}
+int hg_comm_init(hg_handle h, const uint8_t* id, int rank, int world, int ghost_top, int ghost_bottom) {
+    CHECK_H(h);
+    return h->impl->comm_init(id, rank, world, ghost_top, ghost_bottom);
+}
 int hg_reset_guess(hg_handle h) { CHECK_H(h); return h->impl->reset_guess(); }
 int hg_mg_levels(hg_handle h) { CHECK_H(h); return h->impl->mg_levels(); }
 int hg_mg_get_level(hg_handle h, int level, int* rows, int* cols, double* coef9) { CHECK_H(h); return h->impl->mg_get_level(level, rows, cols, coef9); }

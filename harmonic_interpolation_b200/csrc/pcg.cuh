@@ -18,6 +18,7 @@ struct CgState {
     double bb[HG_MAXK];     // ||b_f - A_fc x_c||^2, the reference norm of the stopping rule
     double alpha[HG_MAXK];
     double beta[HG_MAXK];
+    double tmp[HG_MAXK];    // local sums awaiting the allreduce over slabs (multi-GPU)
     double tol2;            // rtol^2: the stopping rule on the TRUE residual (outer check)
     double tol2_eff;        // stopping rule of the current inner CG run (recurrence residual)
     double outer_ratio;     // max_k rr/bb of the true residual at the last outer check
@@ -48,12 +49,23 @@ __device__ __forceinline__ double ordered_sum(const double* part, int n, double*
     return block_sum(s, red);
 }
 
+// Scalar stages.  `phase` 0: sum the partial sums and finish (single GPU).  Multi-GPU splits a
+// stage around an allreduce of CgState::tmp over the slabs: phase 1 only leaves the local sums
+// in tmp, phase 2 finishes from tmp.
+__device__ __forceinline__ double stage_value(CgState* st, const double* part, int nblk, int k, int phase, double* red) {
+    if (phase == 2) return st->tmp[k];
+    const double v = ordered_sum(part + (long long)k * nblk, nblk, red);
+    if (phase == 1 && threadIdx.x == 0) st->tmp[k] = v;
+    return v;
+}
+
 // after q = A p:  alpha = rz / pq
-__global__ void cg_alpha_kernel(CgState* st, const double* __restrict__ part_pq, int nblk, int K) {
+__global__ void cg_alpha_kernel(CgState* st, const double* __restrict__ part_pq, int nblk, int K, int phase) {
     if (st->done) return;
     __shared__ double red[32];
     for (int k = 0; k < K; ++k) {
-        const double pq = ordered_sum(part_pq + (long long)k * nblk, nblk, red);
+        const double pq = stage_value(st, part_pq, nblk, k, phase, red);
+        if (phase == 1) { __syncthreads(); continue; }
         if (threadIdx.x == 0) {
             st->pq[k] = pq;
             double a = 0.0;
@@ -72,7 +84,7 @@ __global__ void cg_alpha_kernel(CgState* st, const double* __restrict__ part_pq,
 // ---- generic (any preconditioner) CG kernels ----------------------------------------------------
 // convergence check right after the x / r update, so that the preconditioner launches that follow
 // turn into no-ops once the tolerance is met
-__global__ void cg_check_kernel(CgState* st, const double* __restrict__ part_rr, int nblk, int K) {
+__global__ void cg_check_kernel(CgState* st, const double* __restrict__ part_rr, int nblk, int K, int phase) {
     if (st->done) return;
     __shared__ double red[32];
     __shared__ int all_conv;
@@ -80,7 +92,8 @@ __global__ void cg_check_kernel(CgState* st, const double* __restrict__ part_rr,
     if (threadIdx.x == 0) { all_conv = 1; worst = 0.0; }
     __syncthreads();
     for (int k = 0; k < K; ++k) {
-        const double rr = ordered_sum(part_rr + (long long)k * nblk, nblk, red);
+        const double rr = stage_value(st, part_rr, nblk, k, phase, red);
+        if (phase == 1) { __syncthreads(); continue; }
         if (threadIdx.x == 0) {
             st->rr[k] = rr;
             if (!(rr == rr)) st->done = 2;
@@ -89,7 +102,7 @@ __global__ void cg_check_kernel(CgState* st, const double* __restrict__ part_rr,
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && phase != 1) {
         st->iter += 1;
         if (all_conv && st->done == 0) st->done = 1;
         if (st->iter >= st->maxiter && st->done == 0) st->done = 4;
@@ -101,14 +114,15 @@ __global__ void cg_check_kernel(CgState* st, const double* __restrict__ part_rr,
 // reference norm bb at the first call, decides final convergence, and arms the next inner CG
 // run, which only has to reduce the residual by `inner_red` (fp32 storage cannot do better).
 __global__ void cg_outer_kernel(CgState* st, const double* __restrict__ part_rr, int nblk, int K, int first,
-                                double inner_red2) {
+                                double inner_red2, int phase) {
     __shared__ double red[32];
     __shared__ int all_conv;
     __shared__ double worst;
     if (threadIdx.x == 0) { all_conv = 1; worst = 0.0; }
     __syncthreads();
     for (int k = 0; k < K; ++k) {
-        const double rr = ordered_sum(part_rr + (long long)k * nblk, nblk, red);
+        const double rr = stage_value(st, part_rr, nblk, k, phase, red);
+        if (phase == 1) { __syncthreads(); continue; }
         if (threadIdx.x == 0) {
             if (first) st->bb[k] = rr;
             st->rr[k] = rr;
@@ -119,7 +133,7 @@ __global__ void cg_outer_kernel(CgState* st, const double* __restrict__ part_rr,
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && phase != 1) {
         st->outer_ratio = worst;
         if (st->done != 2) {
             st->outer_done = all_conv;
@@ -132,11 +146,12 @@ __global__ void cg_outer_kernel(CgState* st, const double* __restrict__ part_rr,
 }
 
 // after z = M^-1 r:  rz_new -> beta
-__global__ void cg_beta_rz_kernel(CgState* st, const double* __restrict__ part_rz, int nblk, int K, int init) {
+__global__ void cg_beta_rz_kernel(CgState* st, const double* __restrict__ part_rz, int nblk, int K, int init, int phase) {
     if (st->done) return;
     __shared__ double red[32];
     for (int k = 0; k < K; ++k) {
-        const double rz = ordered_sum(part_rz + (long long)k * nblk, nblk, red);
+        const double rz = stage_value(st, part_rz, nblk, k, phase, red);
+        if (phase == 1) { __syncthreads(); continue; }
         if (threadIdx.x == 0) {
             st->beta[k] = (!init && st->rz[k] != 0.0) ? rz / st->rz[k] : 0.0;
             st->rz[k] = rz;

@@ -133,6 +133,18 @@ int hg_download(hg_handle h, double* x_out, hg_stats* stats);
  * stay), so that hg_solve_device can be timed repeatedly on the same uploaded values. */
 int hg_reset_guess(hg_handle h);
 
+/* ---- multi-GPU: row slabs of one grid, one process per GPU ------------------------------------
+ * Each process creates its solver on the rows it owns PLUS one ghost row towards each neighbouring
+ * slab (flagged HG_FLAG_HARD, carrying the neighbour's cut / penalty bits of that row), then joins
+ * the communicator.  During a solve the library refreshes the ghost rows of the search direction
+ * and of the iterate from the neighbours (NCCL send / recv over NVLink) before every operator
+ * application and all-reduces the K conjugate-gradient scalars; the multigrid V-cycle acts per
+ * slab (block-Jacobi).  hg_comm_unique_id: 128 bytes from rank 0, to be broadcast by the caller.
+ * Laplacian only. */
+#define HG_COMM_ID_BYTES 128
+int hg_comm_unique_id(uint8_t* id);
+int hg_comm_init(hg_handle h, const uint8_t* id, int rank, int world, int ghost_top, int ghost_bottom);
+
 /* z = M^-1 r: one application of the preconditioner (Jacobi or one multigrid V-cycle) to a
  * host array; r is masked to the free pixels first.  For tests of symmetry / definiteness. */
 int hg_precond_apply(hg_handle h, const double* r, double* z);
