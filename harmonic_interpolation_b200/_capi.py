@@ -58,7 +58,8 @@ SYMBOLS = {
     "hg_download": (ctypes.c_int, [_H, _dp, ctypes.POINTER(Stats)]),
     "hg_reset_guess": (ctypes.c_int, [_H]),
     "hg_comm_unique_id": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint8)]),
-    "hg_comm_init": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "hg_comm_init": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                    ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
     "hg_bench_apply": (ctypes.c_int, [_H, ctypes.c_int, _dp]),
     "hg_precond_apply": (ctypes.c_int, [_H, _dp, _dp]),
     "hg_mg_levels": (ctypes.c_int, [_H]),

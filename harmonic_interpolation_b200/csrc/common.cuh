@@ -8,6 +8,7 @@
 
 #define HG_MAXK 16          // channels solved together; the Python layer chunks beyond this
 #define HG_FULL 0xffffffffu
+#define HG_GATHER_LEVEL 5    // from this level down the hierarchy is replicated on every rank
 
 namespace hg {
 

@@ -55,6 +55,7 @@ struct Nccl {
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -79,6 +80,7 @@ static int nccl_load() {
     HG_SYM(AllReduce, "ncclAllReduce");
     HG_SYM(Send, "ncclSend");
     HG_SYM(Recv, "ncclRecv");
+    HG_SYM(Broadcast, "ncclBroadcast");
     HG_SYM(GroupStart, "ncclGroupStart");
     HG_SYM(GroupEnd, "ncclGroupEnd");
     HG_SYM(GetErrorString, "ncclGetErrorString");
@@ -113,7 +115,7 @@ struct SolverBase {
     virtual int mg_get_level(int level, int* rows, int* cols, double* coef9) = 0;
     virtual int precond_apply(const double* r, double* z) = 0;
     virtual int reset_guess() = 0;
-    virtual int comm_init(const uint8_t* id, int rank, int world, int ghost_top, int ghost_bottom) = 0;
+    virtual int comm_init(const uint8_t* id, int rank, int world, int ghost_top, int ghost_bottom, const int* row_starts, int global_rows) = 0;
 };
 
 template <typename T>
@@ -148,7 +150,10 @@ struct Solver : SolverBase {
     // multi-GPU slab mode: this solver owns a band of rows of a larger grid; the rows directly
     // above / below (ghost rows, flagged hard) mirror the neighbouring slabs
     ncclComm_t comm = nullptr;
-    int rank = 0, world = 1, ghost_top = 0, ghost_bottom = 0;
+    int rank = 0, world = 1, ghost_top = 0, ghost_bottom = 0, global_rows = 0;
+    std::vector<int> row_starts;             // first owned global row of every rank (+ global_rows at the end)
+    std::vector<Coarse<T>> gcoarse;          // replicated global hierarchy from level HG_GATHER_LEVEL down
+    double* d_gdense = nullptr;
 
     // multigrid hierarchy (levels >= 1; level 0 is the flag-encoded operator)
     T* d_z = nullptr;
@@ -306,8 +311,76 @@ struct Solver : SolverBase {
     void free_hierarchy() {
         for (auto& c : coarse) { cudaFree(c.coef); cudaFree(c.x); cudaFree(c.b); }
         coarse.clear();
-        cudaFree(d_dense);
-        d_dense = nullptr;
+        for (auto& c : gcoarse) { cudaFree(c.coef); cudaFree(c.x); cudaFree(c.b); }
+        gcoarse.clear();
+        cudaFree(d_dense); cudaFree(d_gdense);
+        d_dense = d_gdense = nullptr;
+    }
+
+    static int chain(int n, int levels) { for (int l = 0; l < levels; ++l) n = (n + 1) / 2; return n; }
+
+    int alloc_level(Coarse<T>& L, int r, int c) {
+        L.rows = r; L.cols = c;
+        L.pitch = round_up(c, 32);
+        L.plane = (long long)L.rows * L.pitch;
+        L.K = K;
+        L.coef = L.x = L.b = nullptr;
+        CU(cudaMalloc(&L.coef, (size_t)L.plane * 9 * sizeof(T)));
+        CU(cudaMalloc(&L.x, (size_t)L.plane * K * sizeof(T)));
+        CU(cudaMalloc(&L.b, (size_t)L.plane * K * sizeof(T)));
+        CU(cudaMemsetAsync(L.coef, 0, (size_t)L.plane * 9 * sizeof(T), stream));
+        CU(cudaMemsetAsync(L.x, 0, (size_t)L.plane * K * sizeof(T), stream));
+        CU(cudaMemsetAsync(L.b, 0, (size_t)L.plane * K * sizeof(T), stream));
+        return HG_OK;
+    }
+
+    int build_dense(const Coarse<T>& L, double** out) {
+        const int n = L.rows * L.cols;
+        CU(cudaMalloc(out, (size_t)n * 2 * n * sizeof(double)));
+        dense_from_stencil_kernel<T><<<64, 256, 0, stream>>>(L, *out);
+        dense_fill_kernel<T><<<(n + 127) / 128, 128, 0, stream>>>(L, *out);
+        gauss_jordan_kernel<<<1, 1024, 2 * n * sizeof(double), stream>>>(*out, n);
+        return HG_OK;
+    }
+
+    // slab mode: rows of level HG_GATHER_LEVEL owned by rank q, in the replicated global level
+    int gl_start(int q) const { return row_starts[q] >> HG_GATHER_LEVEL; }
+    int gl_end(int q) const { return q == world - 1 ? chain(global_rows, HG_GATHER_LEVEL) : row_starts[q + 1] >> HG_GATHER_LEVEL; }
+
+    // every rank's owned rows of `nplanes` planes of the local gather level -> the global level
+    int gather_level(const T* local, long long lplane, T* global, long long gplane, int pitch_, int nplanes) {
+        const ncclDataType_t dt = sizeof(T) == 8 ? ncclDouble : ncclFloat;
+        const int gtL = ghost_top >> HG_GATHER_LEVEL;
+        NC(g_nccl.GroupStart());
+        for (int c = 0; c < nplanes; ++c)
+            for (int q = 0; q < world; ++q) {
+                T* dst = global + (long long)c * gplane + (long long)gl_start(q) * pitch_;
+                const T* src = q == rank ? local + (long long)c * lplane + (long long)gtL * pitch_ : dst;
+                NC(g_nccl.Broadcast(src, dst, (size_t)(gl_end(q) - gl_start(q)) * pitch_, dt, q, comm, stream));
+            }
+        NC(g_nccl.GroupEnd());
+        return HG_OK;
+    }
+
+    int build_global_hierarchy() {
+        const Coarse<T>& Ll = coarse.back();      // local level HG_GATHER_LEVEL
+        Coarse<T> G;
+        HGTRY(alloc_level(G, chain(global_rows, HG_GATHER_LEVEL), Ll.cols));
+        if (G.pitch != Ll.pitch) return fail(HG_ERR_INVALID, "slab mode: pitch mismatch at the gather level");
+        HGTRY(gather_level(Ll.coef, Ll.plane, G.coef, G.plane, G.pitch, 9));
+        gcoarse.push_back(G);
+        int r = G.rows, c = G.cols;
+        while ((long long)r * c > 256) {
+            Coarse<T> L;
+            HGTRY(alloc_level(L, (r + 1) / 2, (c + 1) / 2));
+            dim3 cg((L.pitch + 127) / 128, L.rows);
+            CoarseAcc<T> ca{gcoarse.back()};
+            galerkin_kernel<T, CoarseAcc<T>><<<cg, 128, 0, stream>>>(ca, L);
+            gcoarse.push_back(L);
+            r = L.rows; c = L.cols;
+        }
+        HGTRY(build_dense(gcoarse.back(), &d_gdense));
+        return HG_OK;
     }
 
     bool use_mg() const { return precond == HG_PRECOND_MULTIGRID && op == HG_OP_LAPLACIAN; }
@@ -350,19 +423,10 @@ struct Solver : SolverBase {
             CU(cudaMalloc(&d_z, (size_t)plane * K * sizeof(T)));
             CU(cudaMemsetAsync(d_z, 0, (size_t)plane * K * sizeof(T), stream));
         }
-        int r = rows, c = cols;
-        while ((long long)r * c > 256) {
+        int r = rows, c = cols, level = 0;
+        while ((long long)r * c > 256 && (world == 1 || level < HG_GATHER_LEVEL)) {
             Coarse<T> L;
-            L.rows = (r + 1) / 2; L.cols = (c + 1) / 2;
-            L.pitch = round_up(L.cols, 32);
-            L.plane = (long long)L.rows * L.pitch;
-            L.K = K;
-            L.coef = L.x = L.b = nullptr;
-            CU(cudaMalloc(&L.coef, (size_t)L.plane * 9 * sizeof(T)));
-            CU(cudaMalloc(&L.x, (size_t)L.plane * K * sizeof(T)));
-            CU(cudaMalloc(&L.b, (size_t)L.plane * K * sizeof(T)));
-            CU(cudaMemsetAsync(L.x, 0, (size_t)L.plane * K * sizeof(T), stream));
-            CU(cudaMemsetAsync(L.b, 0, (size_t)L.plane * K * sizeof(T), stream));
+            HGTRY(alloc_level(L, (r + 1) / 2, (c + 1) / 2));
             dim3 cg((L.pitch + 127) / 128, L.rows);
             if (coarse.empty()) {
                 FineAcc<T> fa{grid()};
@@ -373,52 +437,89 @@ struct Solver : SolverBase {
             }
             coarse.push_back(L);
             r = L.rows; c = L.cols;
+            ++level;
         }
-        if (!coarse.empty()) {
-            const Coarse<T>& L = coarse.back();
-            const int n = L.rows * L.cols;
-            CU(cudaMalloc(&d_dense, (size_t)n * 2 * n * sizeof(double)));
-            dense_from_stencil_kernel<T><<<64, 256, 0, stream>>>(L, d_dense);
-            dense_fill_kernel<T><<<(n + 127) / 128, 128, 0, stream>>>(L, d_dense);
-            gauss_jordan_kernel<<<1, 1024, 2 * n * sizeof(double), stream>>>(d_dense, n);
+        if (world > 1) {
+            if (level < HG_GATHER_LEVEL) return fail(HG_ERR_INVALID, "slab mode: the grid is too small (fewer than HG_GATHER_LEVEL coarse levels)");
+            HGTRY(build_global_hierarchy());
+        } else if (!coarse.empty()) {
+            HGTRY(build_dense(coarse.back(), &d_dense));
         }
         CU(cudaGetLastError());
         return HG_OK;
     }
 
+    void coarse_pre(const Coarse<T>& L, const int* done) {
+        dim3 mg((L.cols / 2 + 1 + 255) / 256, (L.rows + 1) / 2);
+        for (int c = 0; c < 4; ++c) mcgs_kernel<T><<<mg, 256, 0, stream>>>(L, c, done);
+        launches += 4;
+    }
+    void coarse_post(const Coarse<T>& L, const int* done) {
+        dim3 mg((L.cols / 2 + 1 + 255) / 256, (L.rows + 1) / 2);
+        for (int c = 3; c >= 0; --c) mcgs_kernel<T><<<mg, 256, 0, stream>>>(L, c, done);
+        launches += 4;
+    }
+    void coarse_restrict(const Coarse<T>& L, const Coarse<T>& Lc, const int* done) {
+        dim3 gg((Lc.pitch + 255) / 256, Lc.rows);
+        CoarseAcc<T> ca{L};
+        resid_restrict_kernel<T, CoarseAcc<T>><<<gg, 256, 0, stream>>>(ca, L.x, L.b, Lc, K, done);
+        ++launches;
+    }
+    void coarse_prolong(const Coarse<T>& L, const Coarse<T>& Lc, const int* done) {
+        CoarseAcc<T> ca{L};
+        dim3 gg((L.cols + 255) / 256, L.rows);
+        prolong_add_kernel<T, CoarseAcc<T>><<<gg, 256, 0, stream>>>(ca, L.x, Lc, K, done);
+        ++launches;
+    }
+    void coarse_solve(const Coarse<T>& L, const double* dense, const int* done) {
+        const int n = L.rows * L.cols;
+        coarsest_dense_kernel<T><<<K, 256, n * sizeof(double), stream>>>(L, dense, done);
+        ++launches;
+    }
+    // V-cycle over levels[from..] of a hierarchy whose first level already holds b (and x = 0)
+    void coarse_vcycle(const std::vector<Coarse<T>>& lv, const double* dense, const int* done) {
+        const int n = (int)lv.size();
+        for (int l = 0; l + 1 < n; ++l) { coarse_pre(lv[l], done); coarse_restrict(lv[l], lv[l + 1], done); }
+        coarse_solve(lv[n - 1], dense, done);
+        for (int l = n - 2; l >= 0; --l) { coarse_prolong(lv[l], lv[l + 1], done); coarse_post(lv[l], done); }
+    }
+
     // z = M^-1 r : one V(1,1) cycle from a zero initial guess; also leaves the per-tile partial
-    // sums of r.z in part_rz.  Level 0 is two fused tile kernels (fine.cuh).
-    void vcycle(T* z, const T* r, const int* done, double* part_rz) {
+    // sums of r.z in part_rz.  Level 0 is two fused tile kernels (fine.cuh).  In slab mode the
+    // ghost bands are refreshed once per level and leg and levels >= HG_GATHER_LEVEL run replicated.
+    int vcycle(T* z, T* r, const int* done, double* part_rz) {
         const Grid<T> g = grid();
         const int nl = (int)coarse.size();
         if (nl > 0) {
+            if (world > 1) HGTRY(exchange(r, HG_GHOST_ROWS));
             if (has_pen) mg_down0_kernel<T, true><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, DOWN_H, true>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
             else mg_down0_kernel<T, false><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, DOWN_H, false>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
             ++launches;
-            for (int l = 0; l + 1 < nl; ++l) {
-                const Coarse<T>& L = coarse[l];
-                dim3 mg((L.cols / 2 + 1 + 255) / 256, (L.rows + 1) / 2);
-                for (int c = 0; c < 4; ++c) mcgs_kernel<T><<<mg, 256, 0, stream>>>(L, c, done);
-                const Coarse<T>& Lc = coarse[l + 1];
-                dim3 gg((Lc.pitch + 255) / 256, Lc.rows);
-                CoarseAcc<T> ca{L};
-                resid_restrict_kernel<T, CoarseAcc<T>><<<gg, 256, 0, stream>>>(ca, L.x, L.b, Lc, K, done);
-                launches += 5;
-            }
-            {
-                const Coarse<T>& L = coarse[nl - 1];
-                const int n = L.rows * L.cols;
-                coarsest_dense_kernel<T><<<K, 256, n * sizeof(double), stream>>>(L, d_dense, done);
-                ++launches;
-            }
-            for (int l = nl - 2; l >= 0; --l) {
-                const Coarse<T>& L = coarse[l];
-                CoarseAcc<T> ca{L};
-                dim3 gg((L.cols + 255) / 256, L.rows);
-                prolong_add_kernel<T, CoarseAcc<T>><<<gg, 256, 0, stream>>>(ca, L.x, coarse[l + 1], K, done);
-                dim3 mg((L.cols / 2 + 1 + 255) / 256, (L.rows + 1) / 2);
-                for (int c = 3; c >= 0; --c) mcgs_kernel<T><<<mg, 256, 0, stream>>>(L, c, done);
-                launches += 5;
+            if (world == 1) {
+                coarse_vcycle(coarse, d_dense, done);
+            } else {
+                const int Lg = HG_GATHER_LEVEL;
+                for (int l = 0; l + 1 < Lg; ++l) {       // local levels 1 .. Lg-1
+                    HGTRY(exchange_level(coarse[l], l + 1, coarse[l].b, K));
+                    coarse_pre(coarse[l], done);
+                    coarse_restrict(coarse[l], coarse[l + 1], done);
+                }
+                // level Lg: gather the owned rows of b, solve replicated, take back the local window of x
+                const Coarse<T>& Ll = coarse[Lg - 1];
+                const Coarse<T>& G = gcoarse[0];
+                CU(cudaMemsetAsync(G.x, 0, (size_t)G.plane * K * sizeof(T), stream));
+                HGTRY(gather_level(Ll.b, Ll.plane, G.b, G.plane, G.pitch, K));
+                coarse_vcycle(gcoarse, d_gdense, done);
+                const long long off = (long long)((row_starts[rank] - ghost_top) >> Lg) * G.pitch;
+                for (int k = 0; k < K; ++k)
+                    CU(cudaMemcpyAsync(Ll.x + (long long)k * Ll.plane, G.x + (long long)k * G.plane + off,
+                                       (size_t)Ll.plane * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+                for (int l = Lg - 2; l >= 0; --l) {
+                    if (l + 2 < Lg) HGTRY(exchange_level(coarse[l + 1], l + 2, coarse[l + 1].x, K));
+                    coarse_prolong(coarse[l], coarse[l + 1], done);
+                    coarse_post(coarse[l], done);
+                }
+                HGTRY(exchange_level(coarse[0], 1, coarse[0].x, K));
             }
         }
         Coarse<T> c0;
@@ -427,6 +528,7 @@ struct Solver : SolverBase {
         if (has_pen) mg_up0_kernel<T, true><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, UP_H, true>), stream>>>(g, d_code, r, z, c0, nl > 0, d_tile_active, part_rz, done);
         else mg_up0_kernel<T, false><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, UP_H, false>), stream>>>(g, d_code, r, z, c0, nl > 0, d_tile_active, part_rz, done);
         ++launches;
+        return HG_OK;
     }
 
     int mg_levels() override { return 1 + (int)coarse.size(); }
@@ -458,7 +560,7 @@ struct Solver : SolverBase {
         import_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_stage[0], d_r);
         mask_hard_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_r);
         if (use_mg()) {
-            vcycle(d_z, d_r, nullptr, d_tpart1);
+            HGTRY(vcycle(d_z, d_r, nullptr, d_tpart1));
             export_kernel<T, T><<<pg, 256, 0, stream>>>(grid(), d_z, d_out);
         } else {
             jacobi_apply_kernel<T><<<vec_blocks(), VEC_THREADS, 0, stream>>>(plane, K, d_q, d_r, d_dinv);
@@ -589,41 +691,78 @@ struct Solver : SolverBase {
         return HG_OK;
     }
 
-    int comm_init(const uint8_t* id, int rank_, int world_, int gt, int gb) override {
+    // Slab mode.  The local grid is [ghost band | owned rows | ghost band]; ghost bands are
+    // HG_GHOST_ROWS deep MIRRORS of the neighbouring slabs (same flags, same values after a
+    // refresh).  Every kernel simply runs on the whole local grid: what it computes on ghost rows
+    // is redundant with the neighbour and valid up to a few rows from the outer edge, so a whole
+    // smoothing sweep needs no communication and its result on the owned rows is exactly the
+    // single-GPU one.  Ghost bands are refreshed (send / recv) once per level and leg; from level
+    // HG_GATHER_LEVEL down the hierarchy is replicated on every rank.  Dot products run over the
+    // owned tile rows only and are all-reduced.
+    int comm_init(const uint8_t* id, int rank_, int world_, int gt, int gb, const int* starts, int grows) override {
         if (world_ < 1 || rank_ < 0 || rank_ >= world_) return fail(HG_ERR_INVALID, "hg_comm_init: bad rank / world");
+        rank = rank_; world = world_; ghost_top = gt; ghost_bottom = gb; global_rows = grows;
+        if (world == 1) return HG_OK;
         if (op != HG_OP_LAPLACIAN) return fail(HG_ERR_INVALID, "hg_comm_init: the slab mode supports the Laplacian operator only");
-        if (gt < 0 || gt > 1 || gb < 0 || gb > 1 || (rank_ == 0 && gt) || (rank_ == world_ - 1 && gb) || gt + gb >= rows)
-            return fail(HG_ERR_INVALID, "hg_comm_init: bad ghost rows");
-        rank = rank_; world = world_; ghost_top = gt; ghost_bottom = gb;
-        if (world > 1) {
-            if (!id) return fail(HG_ERR_INVALID, "hg_comm_init: NULL id");
-            HGTRY(nccl_load());
-            ncclUniqueId uid;
-            memcpy(&uid, id, sizeof uid);
-            NC(g_nccl.CommInitRank(&comm, world, uid, rank));
+        if (!id || !starts) return fail(HG_ERR_INVALID, "hg_comm_init: NULL id / row_starts");
+        row_starts.assign(starts, starts + world);
+        row_starts.push_back(grows);
+        const int want_t = rank == 0 ? 0 : HG_GHOST_ROWS, want_b = rank == world - 1 ? 0 : HG_GHOST_ROWS;
+        if (gt != want_t || gb != want_b) return fail(HG_ERR_INVALID, "hg_comm_init: ghost bands must be HG_GHOST_ROWS deep towards every neighbour");
+        for (int q = 0; q < world; ++q) {
+            if (row_starts[q] % HG_GHOST_ROWS) return fail(HG_ERR_INVALID, "hg_comm_init: slab boundaries must be multiples of HG_GHOST_ROWS");
+            if (row_starts[q + 1] - row_starts[q] < 2 * HG_GHOST_ROWS) return fail(HG_ERR_INVALID, "hg_comm_init: a slab needs at least 2 HG_GHOST_ROWS rows");
         }
+        if (rows != row_starts[rank + 1] - row_starts[rank] + gt + gb) return fail(HG_ERR_INVALID, "hg_comm_init: local rows do not match the partition");
+        HGTRY(nccl_load());
+        ncclUniqueId uid;
+        memcpy(&uid, id, sizeof uid);
+        NC(g_nccl.CommInitRank(&comm, world, uid, rank));
+        is_setup = false;
         return HG_OK;
     }
 
-    // ghost rows of v (K planes) <- the neighbours' boundary rows
+    // refresh `depth_t` / `depth_b` ghost rows of the planes of `v` from the neighbours' owned rows
+    // (level geometry given by pitch_, plane_, rows_, and the ghost-band depths gt_, gb_ at that level)
     template <typename V>
-    int exchange(V* v) {
+    int exchange_rows(V* v, int nplanes, int pitch_, long long plane_, int rows_, int gt_, int gb_, int depth) {
         if (world <= 1) return HG_OK;
         const ncclDataType_t dt = sizeof(V) == 8 ? ncclDouble : ncclFloat;
         NC(g_nccl.GroupStart());
-        for (int k = 0; k < K; ++k) {
-            V* base = v + (long long)k * plane;
-            if (ghost_top) {
-                NC(g_nccl.Send(base + (long long)ghost_top * pitch, pitch, dt, rank - 1, comm, stream));
-                NC(g_nccl.Recv(base, pitch, dt, rank - 1, comm, stream));
+        for (int k = 0; k < nplanes; ++k) {
+            V* base = v + (long long)k * plane_;
+            if (gt_ > 0) {
+                const int d = std::min(depth, gt_);
+                NC(g_nccl.Send(base + (long long)gt_ * pitch_, (size_t)d * pitch_, dt, rank - 1, comm, stream));
+                NC(g_nccl.Recv(base + (long long)(gt_ - d) * pitch_, (size_t)d * pitch_, dt, rank - 1, comm, stream));
             }
-            if (ghost_bottom) {
-                NC(g_nccl.Send(base + (long long)(rows - 1 - ghost_bottom) * pitch, pitch, dt, rank + 1, comm, stream));
-                NC(g_nccl.Recv(base + (long long)(rows - 1) * pitch, pitch, dt, rank + 1, comm, stream));
+            if (gb_ > 0) {
+                const int d = std::min(depth, gb_);
+                NC(g_nccl.Send(base + (long long)(rows_ - gb_ - d) * pitch_, (size_t)d * pitch_, dt, rank + 1, comm, stream));
+                NC(g_nccl.Recv(base + (long long)(rows_ - gb_) * pitch_, (size_t)d * pitch_, dt, rank + 1, comm, stream));
             }
         }
         NC(g_nccl.GroupEnd());
         return HG_OK;
+    }
+    // level-0 vector, `depth` ghost rows
+    template <typename V>
+    int exchange(V* v, int depth) { return exchange_rows(v, K, pitch, plane, rows, ghost_top, ghost_bottom, depth); }
+    template <typename V>
+    int exchange_level(const Coarse<T>& L, int level, V* v, int nplanes) {
+        return exchange_rows(v, nplanes, L.pitch, L.plane, L.rows, ghost_top >> level, ghost_bottom >> level, HG_GHOST_ROWS);
+    }
+
+    // owned range of the per-tile partial sums (dot products skip the ghost tile rows)
+    int own_ty0() const { return ghost_top / FT_Y; }
+    int own_ty1() const { return ghost_bottom ? (rows - ghost_bottom) / FT_Y : tiles_y; }
+    const double* tile_part(const double* part) const { return part + (long long)own_ty0() * tiles_x; }
+    int n_own_tiles() const { return (own_ty1() - own_ty0()) * tiles_x; }
+    // the stencil kernel has two blocks (of LT_ROWS rows) per tile
+    const double* lap_part(const double* part) const { return part + (long long)(ghost_top / LT_ROWS) * tiles_x; }
+    int n_own_lap() const {
+        const int y1 = ghost_bottom ? (rows - ghost_bottom) / LT_ROWS : (rows + LT_ROWS - 1) / LT_ROWS;
+        return (y1 - ghost_top / LT_ROWS) * tiles_x;
     }
 
     int allreduce_tmp() {
@@ -631,33 +770,34 @@ struct Solver : SolverBase {
         return HG_OK;
     }
 
-    // the four scalar stages; with several slabs each is split around an allreduce of the local sums
-    int stage_alpha(const double* part, int n) {
-        if (world <= 1) { cg_alpha_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, K, 0); return HG_OK; }
-        cg_alpha_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, K, 1);
+    // the four scalar stages; with several slabs each is split around an allreduce of the local sums.
+    // `part` points at the first owned partial of channel 0, `n` owned partials, `stride` per channel.
+    int stage_alpha(const double* part, int n, long long stride) {
+        if (world <= 1) { cg_alpha_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, stride, K, 0); return HG_OK; }
+        cg_alpha_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, stride, K, 1);
         HGTRY(allreduce_tmp());
-        cg_alpha_kernel<<<1, 32, 0, stream>>>(d_state, part, n, K, 2);
+        cg_alpha_kernel<<<1, 32, 0, stream>>>(d_state, part, n, stride, K, 2);
         return HG_OK;
     }
-    int stage_check(const double* part, int n) {
-        if (world <= 1) { cg_check_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, K, 0); return HG_OK; }
-        cg_check_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, K, 1);
+    int stage_check(const double* part, int n, long long stride) {
+        if (world <= 1) { cg_check_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, stride, K, 0); return HG_OK; }
+        cg_check_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, stride, K, 1);
         HGTRY(allreduce_tmp());
-        cg_check_kernel<<<1, 32, 0, stream>>>(d_state, part, n, K, 2);
+        cg_check_kernel<<<1, 32, 0, stream>>>(d_state, part, n, stride, K, 2);
         return HG_OK;
     }
-    int stage_beta(const double* part, int n, int init) {
-        if (world <= 1) { cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, K, init, 0); return HG_OK; }
-        cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, K, init, 1);
+    int stage_beta(const double* part, int n, long long stride, int init) {
+        if (world <= 1) { cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, stride, K, init, 0); return HG_OK; }
+        cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, stride, K, init, 1);
         HGTRY(allreduce_tmp());
-        cg_beta_rz_kernel<<<1, 32, 0, stream>>>(d_state, part, n, K, init, 2);
+        cg_beta_rz_kernel<<<1, 32, 0, stream>>>(d_state, part, n, stride, K, init, 2);
         return HG_OK;
     }
-    int stage_outer(const double* part, int n, int first, double red2) {
-        if (world <= 1) { cg_outer_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, K, first, red2, 0); return HG_OK; }
-        cg_outer_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, K, first, red2, 1);
+    int stage_outer(const double* part, int n, long long stride, int first, double red2) {
+        if (world <= 1) { cg_outer_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, stride, K, first, red2, 0); return HG_OK; }
+        cg_outer_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, stride, K, first, red2, 1);
         HGTRY(allreduce_tmp());
-        cg_outer_kernel<<<1, 32, 0, stream>>>(d_state, part, n, K, first, red2, 2);
+        cg_outer_kernel<<<1, 32, 0, stream>>>(d_state, part, n, stride, K, first, red2, 2);
         return HG_OK;
     }
 
@@ -675,6 +815,7 @@ struct Solver : SolverBase {
         if (maxiter <= 0) maxiter = 100000;
         launches = 0;
         const bool mg = use_mg();
+        if (world > 1 && !mg) return fail(HG_ERR_INVALID, "the slab mode needs the multigrid preconditioner");
         const int nb_op = op_blocks(), nb_vec = vec_blocks();
         const dim3 pg((pitch + 255) / 256, rows);
         const int nb_res = pg.x * pg.y;
@@ -709,18 +850,16 @@ struct Solver : SolverBase {
             // true residual in master precision -> d_r (storage type), ||r||^2 -> state
             if (mg) {
                 // master-precision residual with the tile kernel (x, b in fp64 even in fp32 mode)
-                HGTRY(exchange(d_xm));
+                HGTRY(exchange(d_xm, 1));
                 launch_lap_tile<double, 1, 2>(d_xm, b_is_zero ? nullptr : d_bm, d_r, d_lpart, nullptr);
-                HGTRY(stage_outer(d_lpart, n_lap(), outer == 0, inner_red * inner_red));
+                HGTRY(stage_outer(lap_part(d_lpart), n_own_lap(), n_lap(), outer == 0, inner_red * inner_red));
                 --launches;
             } else if (kRefine) {
-                HGTRY(exchange(d_xm));
                 resid_master_kernel<T><<<pg, 256, 0, stream>>>(g, op == HG_OP_BILAPLACIAN, d_xm, d_bm, d_r, d_part0);
-                HGTRY(stage_outer(d_part0, nb_res, outer == 0, inner_red * inner_red));
+                HGTRY(stage_outer(d_part0, nb_res, nb_res, outer == 0, inner_red * inner_red));
             } else {
-                HGTRY(exchange(e));
                 launch_op<1, 2>(e, d_b, d_r, d_part0, nullptr);
-                HGTRY(stage_outer(d_part0, nb_op, outer == 0, inner_red * inner_red));
+                HGTRY(stage_outer(d_part0, nb_op, nb_op, outer == 0, inner_red * inner_red));
             }
             launches += 2;
             CU(cudaMemcpyAsync(&host, d_state, sizeof host, cudaMemcpyDeviceToHost, stream));
@@ -734,39 +873,38 @@ struct Solver : SolverBase {
             // inner PCG on A e = r, e0 = 0 (fp32 mode) or continuing from x (fp64 mode)
             if (kRefine) CU(cudaMemsetAsync(d_x, 0, vbytes, stream));
             if (mg) {
-                vcycle(d_z, d_r, done, d_tpart1);
-                HGTRY(stage_beta(d_tpart1, nt, 1));
+                HGTRY(vcycle(d_z, d_r, done, d_tpart1));
+                HGTRY(stage_beta(tile_part(d_tpart1), n_own_tiles(), nt, 1));
                 cg_pupdate_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, d_p, d_z, d_tile_active, 1);
                 launches += 2;
             } else {
                 jacobi_apply_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(plane, K, d_z, d_r, d_dinv);
                 cg_dot_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_r, d_z, d_part1);
-                HGTRY(stage_beta(d_part1, nb_vec, 1));
+                HGTRY(stage_beta(d_part1, nb_vec, nb_vec, 1));
                 CU(cudaMemcpyAsync(d_p, d_z, vbytes, cudaMemcpyDeviceToDevice, stream));
                 launches += 4;
             }
             while (true) {
                 for (int s = 0; s < batch; ++s) {
                     if (mg) {
-                        HGTRY(exchange(d_p));
+                        HGTRY(exchange(d_p, 1));
                         launch_lap_tile<T, 0, 1>(d_p, nullptr, d_q, d_lpart, done);
-                        HGTRY(stage_alpha(d_lpart, n_lap()));
+                        HGTRY(stage_alpha(lap_part(d_lpart), n_own_lap(), n_lap()));
                         --launches;
                         cg_update_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, e, d_r, d_p, d_q, d_tile_active, d_tpart0);
-                        HGTRY(stage_check(d_tpart0, nt));
-                        vcycle(d_z, d_r, done, d_tpart1);
-                        HGTRY(stage_beta(d_tpart1, nt, 0));
+                        HGTRY(stage_check(tile_part(d_tpart0), n_own_tiles(), nt));
+                        HGTRY(vcycle(d_z, d_r, done, d_tpart1));
+                        HGTRY(stage_beta(tile_part(d_tpart1), n_own_tiles(), nt, 0));
                         cg_pupdate_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, d_p, d_z, d_tile_active, 0);
                         launches += 6;
                     } else {
-                        HGTRY(exchange(d_p));
                         launch_op<0, 1>(d_p, nullptr, d_q, d_part0, done);
-                        HGTRY(stage_alpha(d_part0, nb_op));
+                        HGTRY(stage_alpha(d_part0, nb_op, nb_op));
                         cg_update_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, e, d_r, d_p, d_q, d_part0);
-                        HGTRY(stage_check(d_part0, nb_vec));
+                        HGTRY(stage_check(d_part0, nb_vec, nb_vec));
                         jacobi_apply_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(plane, K, d_z, d_r, d_dinv);
                         cg_dot_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_r, d_z, d_part1);
-                        HGTRY(stage_beta(d_part1, nb_vec, 0));
+                        HGTRY(stage_beta(d_part1, nb_vec, nb_vec, 0));
                         cg_pupdate_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_p, d_z);
                         launches += 7;
                     }
@@ -936,9 +1074,10 @@ int hg_comm_unique_id(uint8_t* id) {
     memcpy(id, &uid, sizeof uid);
     return HG_OK;
 }
-int hg_comm_init(hg_handle h, const uint8_t* id, int rank, int world, int ghost_top, int ghost_bottom) {
+int hg_comm_init(hg_handle h, const uint8_t* id, int rank, int world, int ghost_top, int ghost_bottom, const int* row_starts,
+                 int global_rows) {
     CHECK_H(h);
-    return h->impl->comm_init(id, rank, world, ghost_top, ghost_bottom);
+    return h->impl->comm_init(id, rank, world, ghost_top, ghost_bottom, row_starts, global_rows);
 }
 int hg_reset_guess(hg_handle h) { CHECK_H(h); return h->impl->reset_guess(); }
 int hg_mg_levels(hg_handle h) { CHECK_H(h); return h->impl->mg_levels(); }

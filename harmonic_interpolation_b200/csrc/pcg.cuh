@@ -52,19 +52,19 @@ __device__ __forceinline__ double ordered_sum(const double* part, int n, double*
 // Scalar stages.  `phase` 0: sum the partial sums and finish (single GPU).  Multi-GPU splits a
 // stage around an allreduce of CgState::tmp over the slabs: phase 1 only leaves the local sums
 // in tmp, phase 2 finishes from tmp.
-__device__ __forceinline__ double stage_value(CgState* st, const double* part, int nblk, int k, int phase, double* red) {
+__device__ __forceinline__ double stage_value(CgState* st, const double* part, int nblk, long long stride, int k, int phase, double* red) {
     if (phase == 2) return st->tmp[k];
-    const double v = ordered_sum(part + (long long)k * nblk, nblk, red);
+    const double v = ordered_sum(part + (long long)k * stride, nblk, red);
     if (phase == 1 && threadIdx.x == 0) st->tmp[k] = v;
     return v;
 }
 
 // after q = A p:  alpha = rz / pq
-__global__ void cg_alpha_kernel(CgState* st, const double* __restrict__ part_pq, int nblk, int K, int phase) {
+__global__ void cg_alpha_kernel(CgState* st, const double* __restrict__ part_pq, int nblk, long long stride, int K, int phase) {
     if (st->done) return;
     __shared__ double red[32];
     for (int k = 0; k < K; ++k) {
-        const double pq = stage_value(st, part_pq, nblk, k, phase, red);
+        const double pq = stage_value(st, part_pq, nblk, stride, k, phase, red);
         if (phase == 1) { __syncthreads(); continue; }
         if (threadIdx.x == 0) {
             st->pq[k] = pq;
@@ -84,7 +84,7 @@ __global__ void cg_alpha_kernel(CgState* st, const double* __restrict__ part_pq,
 // ---- generic (any preconditioner) CG kernels ----------------------------------------------------
 // convergence check right after the x / r update, so that the preconditioner launches that follow
 // turn into no-ops once the tolerance is met
-__global__ void cg_check_kernel(CgState* st, const double* __restrict__ part_rr, int nblk, int K, int phase) {
+__global__ void cg_check_kernel(CgState* st, const double* __restrict__ part_rr, int nblk, long long stride, int K, int phase) {
     if (st->done) return;
     __shared__ double red[32];
     __shared__ int all_conv;
@@ -92,7 +92,7 @@ __global__ void cg_check_kernel(CgState* st, const double* __restrict__ part_rr,
     if (threadIdx.x == 0) { all_conv = 1; worst = 0.0; }
     __syncthreads();
     for (int k = 0; k < K; ++k) {
-        const double rr = stage_value(st, part_rr, nblk, k, phase, red);
+        const double rr = stage_value(st, part_rr, nblk, stride, k, phase, red);
         if (phase == 1) { __syncthreads(); continue; }
         if (threadIdx.x == 0) {
             st->rr[k] = rr;
@@ -113,7 +113,7 @@ __global__ void cg_check_kernel(CgState* st, const double* __restrict__ part_rr,
 // Outer check on the TRUE residual r = b - A x (computed in the master precision): fixes the
 // reference norm bb at the first call, decides final convergence, and arms the next inner CG
 // run, which only has to reduce the residual by `inner_red` (fp32 storage cannot do better).
-__global__ void cg_outer_kernel(CgState* st, const double* __restrict__ part_rr, int nblk, int K, int first,
+__global__ void cg_outer_kernel(CgState* st, const double* __restrict__ part_rr, int nblk, long long stride, int K, int first,
                                 double inner_red2, int phase) {
     __shared__ double red[32];
     __shared__ int all_conv;
@@ -121,7 +121,7 @@ __global__ void cg_outer_kernel(CgState* st, const double* __restrict__ part_rr,
     if (threadIdx.x == 0) { all_conv = 1; worst = 0.0; }
     __syncthreads();
     for (int k = 0; k < K; ++k) {
-        const double rr = stage_value(st, part_rr, nblk, k, phase, red);
+        const double rr = stage_value(st, part_rr, nblk, stride, k, phase, red);
         if (phase == 1) { __syncthreads(); continue; }
         if (threadIdx.x == 0) {
             if (first) st->bb[k] = rr;
@@ -146,11 +146,11 @@ __global__ void cg_outer_kernel(CgState* st, const double* __restrict__ part_rr,
 }
 
 // after z = M^-1 r:  rz_new -> beta
-__global__ void cg_beta_rz_kernel(CgState* st, const double* __restrict__ part_rz, int nblk, int K, int init, int phase) {
+__global__ void cg_beta_rz_kernel(CgState* st, const double* __restrict__ part_rz, int nblk, long long stride, int K, int init, int phase) {
     if (st->done) return;
     __shared__ double red[32];
     for (int k = 0; k < K; ++k) {
-        const double rz = stage_value(st, part_rz, nblk, k, phase, red);
+        const double rz = stage_value(st, part_rz, nblk, stride, k, phase, red);
         if (phase == 1) { __syncthreads(); continue; }
         if (threadIdx.x == 0) {
             st->beta[k] = (!init && st->rz[k] != 0.0) ? rz / st->rz[k] : 0.0;

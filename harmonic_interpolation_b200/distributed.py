@@ -1,13 +1,14 @@
 """Row-slab decomposition of one grid over the GPUs of a box, one process per GPU
 (torch.distributed is the plumbing: rendezvous, the NCCL id broadcast, the exchange of the
-boundary flag rows at setup; the solve itself talks NCCL from inside libhgrid.so).
+boundary flag bands at setup; the solve itself talks NCCL from inside libhgrid.so).
 
-Every rank owns a contiguous band of rows.  Its local solver is built on the band plus one GHOST
-row towards each neighbouring slab.  Ghost rows are flagged hard, so for the local solver they are
-just more Dirichlet pixels: the operator rows of the owned pixels are exactly the rows of the
-global operator (the library refreshes the ghost values from the neighbour before every operator
-application), the preconditioner is the slab's own V-cycle (block-Jacobi over slabs), and the
-K conjugate-gradient scalars are all-reduced.  Laplacian only.
+The global rows are cut at multiples of GHOST_ROWS (128).  Every rank builds its local solver on
+the band it owns plus a GHOST band of 128 rows towards each neighbouring slab.  Ghost rows mirror
+the neighbour: same flags and soft weights, values refreshed by the library during the solve.
+All kernels run unchanged on the local grid; what they compute on ghost rows is redundant with
+the neighbour, so a whole smoothing sweep needs no communication and the V-cycle is the
+single-GPU V-cycle (iteration counts do not depend on the number of slabs).  Dot products run
+over owned rows and are all-reduced.  Laplacian only.
 """
 import ctypes
 
@@ -16,45 +17,44 @@ import numpy as np
 from . import _capi as C
 from .solver import GridSolver
 
+GHOST_ROWS = 128
 
-def partition_rows(rows, world):
-    """Balanced contiguous bands: list of (row0, row1) per rank."""
-    assert rows >= world >= 1
-    base, extra = divmod(rows, world)
+
+def partition_rows(rows, world, align=GHOST_ROWS):
+    """Contiguous bands cut at multiples of `align`: list of (row0, row1) per rank.  Every band has
+    at least 2*align rows; the last one takes the remainder."""
+    assert world >= 1
+    if world == 1:
+        return [(0, rows)]
+    nblocks = rows // align
+    assert nblocks >= 2 * world, "grid too small for %d slabs (needs >= %d rows)" % (world, 2 * align * world)
+    base, extra = divmod(nblocks, world)
     out, r = [], 0
     for k in range(world):
-        n = base + (1 if k < extra else 0)
-        out.append((r, r + n))
-        r += n
+        n = (base + (1 if k < extra else 0)) * align
+        r1 = rows if k == world - 1 else r + n
+        out.append((r, r1))
+        r = r1
     return out
 
 
-def local_flags_with_ghosts(flags_owned, row_above, row_below):
-    """Stacks [ghost row above | owned rows | ghost row below].  A ghost row keeps the neighbour's
-    edge bits (its CUT_DOWN / PEN_DOWN bits describe the edge into our first row) and is made hard."""
-    parts = []
-    if row_above is not None:
-        parts.append((np.asarray(row_above, np.uint8) | np.uint8(C.FLAG_HARD))[None, :] & np.uint8(~C.FLAG_SOFT & 0xFF))
-    parts.append(np.asarray(flags_owned, np.uint8))
-    if row_below is not None:
-        parts.append((np.asarray(row_below, np.uint8) | np.uint8(C.FLAG_HARD))[None, :] & np.uint8(~C.FLAG_SOFT & 0xFF))
-    return np.ascontiguousarray(np.concatenate(parts, axis=0))
-
-
-def exchange_boundary_rows(first_row, last_row, rank, world, dist, device=None):
-    """All-gathers every rank's first and last owned flag row; returns (row_above, row_below) for
-    this rank (None at the ends).  Works on the gloo (CPU) and nccl (GPU) back ends."""
+def exchange_bands(first_band, last_band, rank, world, dist, device=None):
+    """All-gathers every rank's first and last owned band (GHOST_ROWS rows each); returns
+    (band_above, band_below) for this rank (None at the ends).  gloo (CPU) or nccl (GPU) back end."""
     import torch
-    cols = len(first_row)
-    mine = torch.from_numpy(np.stack([first_row, last_row]).astype(np.uint8))
+    mine = torch.from_numpy(np.ascontiguousarray(np.stack([first_band, last_band])))
     if device is not None:
         mine = mine.to(device)
     bufs = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(bufs, mine)
     above = bufs[rank - 1][1].cpu().numpy() if rank > 0 else None
     below = bufs[rank + 1][0].cpu().numpy() if rank < world - 1 else None
-    assert above is None or len(above) == cols
     return above, below
+
+
+def with_ghost_bands(owned, above, below):
+    parts = [p for p in (above, owned, below) if p is not None]
+    return np.ascontiguousarray(np.concatenate(parts, axis=0))
 
 
 class SlabSolver:
@@ -68,14 +68,20 @@ class SlabSolver:
                  soft_scalar=0.0, w_g=0.0, device=None):
         self.rank = dist.get_rank() if dist is not None else 0
         self.world = dist.get_world_size() if dist is not None else 1
-        self.row0, self.row1 = partition_rows(global_rows, self.world)[self.rank]
+        parts = partition_rows(global_rows, self.world)
+        self.row0, self.row1 = parts[self.rank]
         flags_owned = np.ascontiguousarray(flags_owned, np.uint8)
         assert flags_owned.shape == (self.row1 - self.row0, cols)
-        above = below = None
+        G = GHOST_ROWS
+        above = below = sw_above = sw_below = None
         if self.world > 1:
-            above, below = exchange_boundary_rows(flags_owned[0], flags_owned[-1], self.rank, self.world, dist, device)
-        self.gt, self.gb = int(above is not None), int(below is not None)
-        flags = local_flags_with_ghosts(flags_owned, above, below)
+            above, below = exchange_bands(flags_owned[:G], flags_owned[-G:], self.rank, self.world, dist, device)
+            if soft_weights_owned is not None:
+                sw = np.ascontiguousarray(soft_weights_owned, np.float64)
+                sw_above, sw_below = exchange_bands(sw[:G], sw[-G:], self.rank, self.world, dist, device)
+        self.gt = 0 if above is None else G
+        self.gb = 0 if below is None else G
+        flags = with_ghost_bands(flags_owned, above, below)
         self.local_rows = flags.shape[0]
         self.cols, self.K = cols, channels
         self.solver = GridSolver(self.local_rows, cols, channels, False, precision, "multigrid")
@@ -89,20 +95,24 @@ class SlabSolver:
                 t = t.to(device)
             dist.broadcast(t, 0)
             ident = np.ascontiguousarray(t.cpu().numpy())
+            starts = np.ascontiguousarray([p[0] for p in parts], np.int32)
             C.check(C.lib().hg_comm_init(self.solver._h, ident.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
-                                         self.rank, self.world, self.gt, self.gb))
-        sw = None
+                                         self.rank, self.world, self.gt, self.gb,
+                                         starts.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), int(global_rows)))
+        sw_local = None
         if soft_weights_owned is not None:
-            sw = self._pad(np.asarray(soft_weights_owned, float)[:, :, None])[:, :, 0]
-        self.info = self.solver.set_pattern(flags, sw, soft_scalar, w_g)
+            sw_local = with_ghost_bands(np.asarray(soft_weights_owned, np.float64), sw_above, sw_below)
+        self.info = self.solver.set_pattern(flags, sw_local, soft_scalar, w_g)
 
     def _pad(self, a):
-        """(owned, cols, K) -> (local rows, cols, K) with zero ghost rows."""
+        """(owned, cols, K) -> (local rows, cols, K); ghost rows are left 0 (the library fills them)."""
         if a is None:
             return None
         a = np.asarray(a, np.float64)
         if a.ndim == 2:
             a = a[:, :, None]
+        if self.gt == 0 and self.gb == 0:
+            return a
         out = np.zeros((self.local_rows, self.cols, a.shape[2]))
         out[self.gt:self.gt + a.shape[0]] = a
         return out

@@ -134,16 +134,22 @@ int hg_download(hg_handle h, double* x_out, hg_stats* stats);
 int hg_reset_guess(hg_handle h);
 
 /* ---- multi-GPU: row slabs of one grid, one process per GPU ------------------------------------
- * Each process creates its solver on the rows it owns PLUS one ghost row towards each neighbouring
- * slab (flagged HG_FLAG_HARD, carrying the neighbour's cut / penalty bits of that row), then joins
- * the communicator.  During a solve the library refreshes the ghost rows of the search direction
- * and of the iterate from the neighbours (NCCL send / recv over NVLink) before every operator
- * application and all-reduces the K conjugate-gradient scalars; the multigrid V-cycle acts per
- * slab (block-Jacobi).  hg_comm_unique_id: 128 bytes from rank 0, to be broadcast by the caller.
- * Laplacian only. */
+ * The global rows are cut into bands at multiples of HG_GHOST_ROWS.  Each process creates its
+ * solver on the band it owns PLUS a ghost band of HG_GHOST_ROWS rows towards each neighbouring
+ * slab; the ghost rows MIRROR the neighbour (same flags / soft weights; values are refreshed by
+ * the library).  After hg_comm_init, hg_setup builds the local hierarchy down to level 5 and a
+ * replicated global hierarchy below it; during a solve the library refreshes ghost bands over
+ * NCCL send / recv (NVLink) once per level and leg of the V-cycle and before every operator
+ * application, gathers the level-5 right-hand side, and all-reduces the K conjugate-gradient
+ * scalars.  The V-cycle computed this way is the single-GPU V-cycle: iteration counts do not
+ * depend on the number of slabs.  hg_comm_unique_id: HG_COMM_ID_BYTES bytes from rank 0, to be
+ * broadcast by the caller.  row_starts: first owned global row of every rank (world entries).
+ * Laplacian + multigrid only. */
 #define HG_COMM_ID_BYTES 128
+#define HG_GHOST_ROWS 128
 int hg_comm_unique_id(uint8_t* id);
-int hg_comm_init(hg_handle h, const uint8_t* id, int rank, int world, int ghost_top, int ghost_bottom);
+int hg_comm_init(hg_handle h, const uint8_t* id, int rank, int world, int ghost_top, int ghost_bottom,
+                 const int* row_starts, int global_rows);
 
 /* z = M^-1 r: one application of the preconditioner (Jacobi or one multigrid V-cycle) to a
  * host array; r is masked to the free pixels first.  For tests of symmetry / definiteness. */
