@@ -110,3 +110,17 @@ def test_normals_to_gradients():
     assert abs(d[(0, 0)] + 0.75) < 1e-15 and (2, 2) in d
     e = {(i, j): v for i, j, v in dy}
     assert abs(e[(2, 2)] + 0.75) < 1e-15
+
+
+def test_compat_modules_export_reference_names():
+    """`from recovery import solve_grid_linear, solve_grid_linear_simple` (fill_alpha_harmonic.py:4) keeps working."""
+    import subprocess
+    import sys
+    code = ("import recovery, fill_alpha_harmonic, highlighting, tictoc;"
+            "from recovery import solve_grid_linear, solve_grid_linear_simple, solve_grid_linear_simple3, "
+            "solve_grid_linear_simple3_solver, smooth_bumps, smooth_bumps2, cut_edges_from_mask, "
+            "zero_dx_dy_constraints_from_cut_edges, convert_grid_normal_constraints_to_dx_and_dy_constraints, normalize_to_char_img;"
+            "from highlighting import grow, shrink; from tictoc import tic, toc; print('ok')")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, os.path.join(ROOT, "harmonic_interpolation_b200", "compat")]))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/tmp")
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr
