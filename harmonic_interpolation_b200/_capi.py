@@ -53,6 +53,7 @@ SYMBOLS = {
     "hg_setup": (ctypes.c_int, [_H, ctypes.POINTER(SetupInfo)]),
     "hg_apply": (ctypes.c_int, [_H, _dp, _dp]),
     "hg_solve": (ctypes.c_int, [_H, ctypes.POINTER(Values), _dp, ctypes.c_double, ctypes.c_int, ctypes.POINTER(Stats)]),
+    "hg_solve_u8": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_uint8), ctypes.c_double, ctypes.c_int, ctypes.POINTER(Stats)]),
     "hg_upload_values": (ctypes.c_int, [_H, ctypes.POINTER(Values), ctypes.POINTER(Stats)]),
     "hg_solve_device": (ctypes.c_int, [_H, ctypes.c_double, ctypes.c_int, ctypes.POINTER(Stats)]),
     "hg_download": (ctypes.c_int, [_H, _dp, ctypes.POINTER(Stats)]),

@@ -115,6 +115,8 @@ struct SolverBase {
     virtual int mg_get_level(int level, int* rows, int* cols, double* coef9) = 0;
     virtual int precond_apply(const double* r, double* z) = 0;
     virtual int reset_guess() = 0;
+    virtual int upload_u8(const uint8_t* vals, hg_stats* st) = 0;
+    virtual int download_u8(uint8_t* out, hg_stats* st) = 0;
     virtual int comm_init(const uint8_t* id, int rank, int world, int ghost_top, int ghost_bottom, const int* row_starts, int global_rows) = 0;
 };
 
@@ -950,6 +952,45 @@ struct Solver : SolverBase {
         return HG_OK;
     }
 
+    uint8_t* d_u8 = nullptr;
+
+    int upload_u8(const uint8_t* vals, hg_stats* st) override {
+        if (!is_setup) return fail(HG_ERR_INVALID, "hg_solve_u8: hg_setup has not been called");
+        if (!vals) return fail(HG_ERR_INVALID, "hg_solve_u8: NULL values");
+        const size_t bytes = (size_t)rows * cols * K;
+        if (!d_u8) CU(cudaMalloc(&d_u8, bytes));
+        CU(cudaEventRecord(ev0, stream));
+        CU(cudaMemcpyAsync(d_u8, vals, bytes, cudaMemcpyHostToDevice, stream));
+        dim3 pg((pitch + 255) / 256, rows);
+        build_problem_u8_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_u8, d_xm, d_bm, b_is_zero ? 0 : 1);
+        b_is_zero = true;
+        CU(cudaEventRecord(ev1, stream));
+        CU(cudaStreamSynchronize(stream));
+        CU(cudaGetLastError());
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ev0, ev1));
+        if (st) st->upload_ms = ms;
+        have_values = true;
+        return HG_OK;
+    }
+
+    int download_u8(uint8_t* out, hg_stats* st) override {
+        if (!out) return fail(HG_ERR_INVALID, "hg_solve_u8: NULL output");
+        const size_t bytes = (size_t)rows * cols * K;
+        if (!d_u8) CU(cudaMalloc(&d_u8, bytes));
+        CU(cudaEventRecord(ev0, stream));
+        dim3 pg((pitch + 255) / 256, rows);
+        export_u8_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_xm, d_u8);
+        CU(cudaMemcpyAsync(out, d_u8, bytes, cudaMemcpyDeviceToHost, stream));
+        CU(cudaEventRecord(ev1, stream));
+        CU(cudaStreamSynchronize(stream));
+        CU(cudaGetLastError());
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ev0, ev1));
+        if (st) st->download_ms = ms;
+        return HG_OK;
+    }
+
     int reset_guess() override {
         if (!is_setup || !have_values) return fail(HG_ERR_INVALID, "hg_reset_guess: values have not been uploaded");
         dim3 pg((pitch + 255) / 256, rows);
@@ -1082,6 +1123,19 @@ int hg_comm_init(hg_handle h, const uint8_t* id, int rank, int world, int ghost_
 int hg_reset_guess(hg_handle h) { CHECK_H(h); return h->impl->reset_guess(); }
 int hg_mg_levels(hg_handle h) { CHECK_H(h); return h->impl->mg_levels(); }
 int hg_mg_get_level(hg_handle h, int level, int* rows, int* cols, double* coef9) { CHECK_H(h); return h->impl->mg_get_level(level, rows, cols, coef9); }
+
+int hg_solve_u8(hg_handle h, const uint8_t* hard_vals, uint8_t* out, double rtol, int maxiter, hg_stats* stats) {
+    CHECK_H(h);
+    hg_stats local;
+    memset(&local, 0, sizeof local);
+    hg_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof *st);
+    HGTRY(h->impl->upload_u8(hard_vals, st));
+    int rc = h->impl->solve_device(rtol, maxiter, st);
+    if (rc != HG_OK && rc != HG_ERR_NOT_CONVERGED) return rc;
+    HGTRY(h->impl->download_u8(out, st));
+    return rc;
+}
 
 int hg_solve(hg_handle h, const hg_values* vals, double* x_out, double rtol, int maxiter, hg_stats* stats) {
     CHECK_H(h);

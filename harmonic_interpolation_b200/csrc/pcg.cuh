@@ -320,6 +320,32 @@ __global__ void build_problem_kernel(Grid<T> g, const double* __restrict__ hard_
     }
 }
 
+// uint8 images (the CLI's data, fill_alpha_harmonic.py:27-45): x = u8 / 255 at hard pixels, 0 elsewhere,
+// b = 0;  and back: u8 = clip(round_half_even(255 x), 0, 255)
+template <typename T>
+__global__ void build_problem_u8_kernel(Grid<T> g, const uint8_t* __restrict__ vals, double* __restrict__ x, double* __restrict__ b,
+                                        int zero_b) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= g.pitch) return;
+    const long long o = (long long)i * g.pitch + j;
+    const bool hard = j < g.cols && (g.flags[o] & HG_FLAG_HARD);
+    const long long h = ((long long)i * g.cols + j) * g.K;
+    for (int k = 0; k < g.K; ++k) {
+        x[k * g.plane + o] = hard ? (double)vals[h + k] / 255.0 : 0.0;
+        if (zero_b) b[k * g.plane + o] = 0.0;
+    }
+}
+template <typename T>
+__global__ void export_u8_kernel(Grid<T> g, const double* __restrict__ x, uint8_t* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= g.cols) return;
+    const long long o = (long long)i * g.pitch + j;
+    const long long h = ((long long)i * g.cols + j) * g.K;
+    for (int k = 0; k < g.K; ++k) out[h + k] = (uint8_t)fmin(fmax(rint(x[k * g.plane + o] * 255.0), 0.0), 255.0);
+}
+
 // planar -> (rows, cols, K) float64
 template <typename T, typename TI>
 __global__ void export_kernel(Grid<T> g, const TI* __restrict__ x, double* __restrict__ out) {

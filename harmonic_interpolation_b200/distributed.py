@@ -138,3 +138,20 @@ class SlabSolver:
                                 rtol=rtol, maxiter=maxiter)
         self.last_stats = self.solver.last_stats
         return self._owned(out)
+
+    # ---- image form: bytes both ways, caller-provided (pinned) local buffers -----------------------
+    def pinned_u8(self):
+        """A page-locked uint8 (local rows, cols, K) buffer and its view of the owned rows."""
+        import torch
+        t = torch.empty((self.local_rows, self.cols, self.K), dtype=torch.uint8).pin_memory()
+        a = t.numpy()
+        a[...] = 0
+        self._keep = getattr(self, "_keep", []) + [t]
+        return a, self._owned(a)
+
+    def solve_u8(self, inp_local, out_local, rtol=None, maxiter=None):
+        """hg_solve_u8 on local-sized buffers (ghost rows of the input are ignored: the library fills
+        them); returns the owned rows of `out_local`."""
+        self.solver.solve_u8(inp_local, out_local, rtol=rtol, maxiter=maxiter)
+        self.last_stats = self.solver.last_stats
+        return self._owned(out_local)

@@ -25,6 +25,23 @@ def fill_alpha_harmonic(arr, mask, **solver_kwargs):
     return solve_grid_linear_simple(arr.shape[0], arr.shape[1], value_constraints=(mask, arr), **solver_kwargs)
 
 
+def fill_rgba8(rgba, precision=None, rtol=None):
+    """The CLI's array pipeline in one call (fill_alpha_harmonic.py:72-76): uint8 RGBA (rows, cols, 4)
+    in, uint8 RGB out; keep-mask alpha == 255; pixels travel as bytes both ways and are scaled /
+    rounded on the device exactly as `u8 / 255.` and `(255 x).round(0).clip(0, 255)` do."""
+    from .solver import GridSolver, encode_flags
+    rgba = np.asarray(rgba, dtype=np.uint8)
+    assert rgba.ndim == 3 and rgba.shape[2] == 4
+    rows, cols = rgba.shape[:2]
+    keep = rgba[:, :, 3] == 255
+    assert keep.any()
+    s = GridSolver(rows, cols, 3, False, precision)
+    s.set_pattern(encode_flags(rows, cols, hard=keep))
+    out = s.solve_u8(np.ascontiguousarray(rgba[:, :, :3]), rtol=rtol)
+    s.close()
+    return out
+
+
 def load_img2arr(path):
     """fill_alpha_harmonic.py:27-36: image -> float64 (rows, cols, RGBA) in [0, 1]."""
     from PIL import Image

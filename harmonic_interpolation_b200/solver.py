@@ -141,6 +141,30 @@ class GridSolver:
             C.check(code)
         return out
 
+    def solve_u8(self, hard_vals_u8, out=None, rtol=None, maxiter=None):
+        """Image form (hg_solve_u8): uint8 (rows, cols, K) in -- meaning u8 / 255 at hard pixels -- and
+        uint8 out = clip(round(255 x)).  `out` may be a preallocated (e.g. pinned) uint8 array."""
+        v = np.ascontiguousarray(hard_vals_u8, dtype=np.uint8).reshape(self.rows, self.cols, self.K)
+        if out is None:
+            out = np.empty((self.rows, self.cols, self.K), np.uint8)
+        assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"] and out.size == v.size
+        stats = C.Stats()
+        if rtol is None:
+            rtol = default_rtol(self.precision)
+        if maxiter is None:
+            maxiter = max(2000, 40 * (self.rows + self.cols))
+        p8 = ctypes.POINTER(ctypes.c_uint8)
+        code = self._lib.hg_solve_u8(self._h, v.ctypes.data_as(p8), out.ctypes.data_as(p8), float(rtol), int(maxiter), ctypes.byref(stats))
+        self.last_stats = stats.as_dict()
+        if code == C.ERR_BREAKDOWN:
+            raise ArithmeticError(C.last_error())
+        if code == C.ERR_NOT_CONVERGED:
+            if stats.relres > accept_relres(self.precision):
+                raise ArithmeticError("%s (relative residual %.3e after %d iterations)" % (C.last_error(), stats.relres, stats.iterations))
+        else:
+            C.check(code)
+        return out
+
     # ---- three-step form used by bench.py ---------------------------------------------------
     def upload(self, hard_vals=None, soft_vals=None, d_down=None, d_right=None, x0=None):
         keep = [self._vals(a) for a in (hard_vals, soft_vals, d_down, d_right, x0)]

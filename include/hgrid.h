@@ -125,6 +125,12 @@ int hg_apply(hg_handle h, const double* x, double* y);
  * (recovery.py:926-943, 993, 1059-1075, 1319-1327).  x_out is (rows, cols, K) float64. */
 int hg_solve(hg_handle h, const hg_values* vals, double* x_out, double rtol, int maxiter, hg_stats* stats);
 
+/* Image form of hg_solve for hard-constraint fills (the CLI's pipeline, fill_alpha_harmonic.py:27-45,
+ * 72-76): hard values arrive as uint8 (rows, cols, K) and mean u8 / 255; the result is returned as
+ * uint8 = clip(round_half_even(255 x), 0, 255).  Soft / gradient value arrays are taken as zero.
+ * Moves 1 byte per pixel and channel each way instead of 8. */
+int hg_solve_u8(hg_handle h, const uint8_t* hard_vals, uint8_t* out, double rtol, int maxiter, hg_stats* stats);
+
 /* The same in three steps, so that a benchmark can time the device-resident solve. */
 int hg_upload_values(hg_handle h, const hg_values* vals, hg_stats* stats);
 int hg_solve_device(hg_handle h, double rtol, int maxiter, hg_stats* stats);

@@ -139,6 +139,19 @@ def test_fill_golden_png_fp32():
     assert np.abs(out.astype(int) - exp.astype(int)).max() <= 1
 
 
+def test_fill_rgba8_golden_png():
+    """uint8 in / uint8 out entry point (hg_solve_u8) on the golden image, fp64 and fp32: <= 1 LSB; kept pixels exact."""
+    rgba = np.asarray(Image.open(os.path.join(GOLDEN, "fill_alpha_harmonic_test.png")).convert("RGBA"))
+    exp = np.asarray(Image.open(os.path.join(GOLDEN, "fill_alpha_harmonic_expected.png")))
+    for prec in ("fp64", "fp32"):
+        out = F.fill_rgba8(rgba, precision=prec)
+        assert out.dtype == np.uint8 and out.shape == exp.shape
+        assert np.abs(out.astype(int) - exp.astype(int)).max() <= 1
+        keep = rgba[:, :, 3] == 255
+        assert (out[keep] == rgba[:, :, :3][keep]).all()
+    assert (go.fill_rgba8(rgba) == exp).all()
+
+
 def test_ktest_all_ones():
     """fill_alpha_harmonic.py:85-99: a hole in an all-ones image fills with ones."""
     for sl in (np.s_[:3, :3], np.s_[3:6, 3:6]):
