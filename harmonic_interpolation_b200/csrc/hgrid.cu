@@ -2,6 +2,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <nccl.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -12,6 +13,7 @@
 
 #include "common.cuh"
 #include "fine.cuh"
+#include "fine_vec.cuh"
 #include "mg.cuh"
 #include "pcg.cuh"
 #include "stencil.cuh"
@@ -168,6 +170,7 @@ struct Solver : SolverBase {
     uint8_t* d_down_active = nullptr;   // tiles with a free pixel within one pixel (restriction reaches that far)
     uint8_t* d_code = nullptr;          // one byte of edge-weight codes per pixel (fine.cuh)
     double* d_lpart = nullptr;          // partial sums of the stencil kernel (two blocks per tile)
+    bool scalar_legs = getenv("HGRID_SCALAR_LEGS") != nullptr;   // debugging aid: the scalar fused legs of fine.cuh
     bool b_is_zero = false;             // no soft / gradient constraints: the right-hand side is identically 0
     bool has_pen = false;
 
@@ -415,6 +418,8 @@ struct Solver : SolverBase {
         CU(cudaFuncSetAttribute(mg_down0_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, DOWN_H, true>)));
         CU(cudaFuncSetAttribute(mg_up0_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, UP_H, false>)));
         CU(cudaFuncSetAttribute(mg_up0_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, UP_H, true>)));
+        CU(cudaFuncSetAttribute(mg_down0v_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VRegionSmem<T>)));
+        CU(cudaFuncSetAttribute(mg_up0v_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VRegionSmem<T>)));
         return HG_OK;
     }
 
@@ -495,7 +500,8 @@ struct Solver : SolverBase {
         if (nl > 0) {
             if (world > 1) HGTRY(exchange(r, HG_GHOST_ROWS));
             if (has_pen) mg_down0_kernel<T, true><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, DOWN_H, true>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
-            else mg_down0_kernel<T, false><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, DOWN_H, false>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
+            else if (scalar_legs) mg_down0_kernel<T, false><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, DOWN_H, false>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
+            else mg_down0v_kernel<T><<<tile_grid(), VR_THREADS, sizeof(VRegionSmem<T>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
             ++launches;
             if (world == 1) {
                 coarse_vcycle(coarse, d_dense, done);
@@ -528,7 +534,8 @@ struct Solver : SolverBase {
         memset(&c0, 0, sizeof c0);
         if (nl > 0) c0 = coarse[0];
         if (has_pen) mg_up0_kernel<T, true><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, UP_H, true>), stream>>>(g, d_code, r, z, c0, nl > 0, d_tile_active, part_rz, done);
-        else mg_up0_kernel<T, false><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, UP_H, false>), stream>>>(g, d_code, r, z, c0, nl > 0, d_tile_active, part_rz, done);
+        else if (scalar_legs) mg_up0_kernel<T, false><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, UP_H, false>), stream>>>(g, d_code, r, z, c0, nl > 0, d_tile_active, part_rz, done);
+        else mg_up0v_kernel<T><<<tile_grid(), VR_THREADS, sizeof(VRegionSmem<T>), stream>>>(g, d_code, r, z, c0, nl > 0, d_tile_active, part_rz, done);
         ++launches;
         return HG_OK;
     }
