@@ -64,6 +64,7 @@ __device__ __forceinline__ void sts2(double* p, double a, double b) { *reinterpr
 template <typename T>
 __device__ __forceinline__ T dinv_of(const Grid<T>& g, unsigned c, unsigned f, long long o) {
     if (f & HG_FLAG_HARD) return T(0);
+    if (c == 0xAAu && !(f & HG_FLAG_SOFT)) return T(1);
     T d = T(0.125) * T((c & 3u) + ((c >> 2) & 3u) + ((c >> 4) & 3u) + ((c >> 6) & 3u));
     if (f & HG_FLAG_SOFT) d += soft_w(g, o, f);
     return d > T(0) ? T(1) / d : T(0);
@@ -103,18 +104,44 @@ __device__ __forceinline__ void vregion_build_op(const Grid<T>& g, const uint8_t
     }
 }
 
+// Load geometry of a thread, computed once per tile: the (up to) two float4 it fetches per channel.
+struct VLoadSlot {
+    long long off[2];     // element offset in the plane, -1 = outside the grid (zeros)
+    int first[2];         // smem element index (row * VR_SW + col) of the quad's first-colour pair
+    int odd[2];           // row parity: which colour comes first
+    int n;
+};
+__device__ __forceinline__ VLoadSlot vregion_load_slots(int rows, int pitch, int gi0, int gj0) {
+    VLoadSlot L;
+    L.n = 0;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int e = threadIdx.x + it * VR_THREADS;
+        L.off[it] = -1; L.first[it] = 0; L.odd[it] = 0;
+        if (e < VR_RH * (VR_W / 4)) {
+            const int li = e / (VR_W / 4), u = e - li * (VR_W / 4);
+            const int i = gi0 + li, j = gj0 + 4 * u;
+            if (i >= 0 && i < rows && j >= 0 && j < pitch) L.off[it] = (long long)i * pitch + j;
+            L.first[it] = (li + 1) * VR_SW + 2 * u + 4;
+            L.odd[it] = li & 1;
+            L.n = it + 1;
+        }
+    }
+    return L;
+}
 // one channel of a value plane -> colour-split arrays, aligned float4 loads
 template <typename T>
-__device__ __forceinline__ void vregion_load(const T* __restrict__ v, const Grid<T>& g, int gi0, int gj0,
-                                             T (*red)[VR_SW], T (*blk)[VR_SW]) {
-    for (int e = threadIdx.x; e < VR_RH * (VR_W / 4); e += VR_THREADS) {
-        const int li = e / (VR_W / 4), u = e - li * (VR_W / 4);
-        const int i = gi0 + li, j = gj0 + 4 * u;
-        V4<T> x = zero4<T>();
-        if (i >= 0 && i < g.rows && j >= 0 && j < g.pitch) x = ld4(v + (long long)i * g.pitch + j);
-        const int a = li + 1, t = 2 * u + 4;
-        if (li & 1) { sts2(&blk[a][t], x.v[0], x.v[2]); sts2(&red[a][t], x.v[1], x.v[3]); }
-        else        { sts2(&red[a][t], x.v[0], x.v[2]); sts2(&blk[a][t], x.v[1], x.v[3]); }
+__device__ __forceinline__ void vregion_load(const T* __restrict__ v, const VLoadSlot& L, T* red, T* blk) {
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        if (it < L.n) {
+            V4<T> x = zero4<T>();
+            if (L.off[it] >= 0) x = ld4(v + L.off[it]);
+            T* p0 = (L.odd[it] ? blk : red) + L.first[it];
+            T* p1 = (L.odd[it] ? red : blk) + L.first[it];
+            sts2(p0, x.v[0], x.v[2]);
+            sts2(p1, x.v[1], x.v[3]);
+        }
     }
 }
 
@@ -130,7 +157,10 @@ __device__ __forceinline__ Q4<T> vregion_nsum(const T (*other)[VR_SW], const uin
     else   { lf[0] = ex; lf[1] = mid.v[0]; lf[2] = mid.v[1]; lf[3] = mid.v[2]; rt[0] = mid.v[0]; rt[1] = mid.v[1]; rt[2] = mid.v[2]; rt[3] = mid.v[3]; }
     const unsigned c4 = *reinterpret_cast<const unsigned*>(&codes[a][c]);
     Q4<T> out;
-    if (c4 == 0xAAAAAAAAu) {
+    // fast path: every pixel of the quad is regular (code 0xAA) or dead (code 0x00: its value is
+    // forced to 0 by the caller through dinv == 0, whatever is computed here)
+    const unsigned hi = c4 & 0xAAAAAAAAu;
+    if ((c4 & 0x55555555u) == 0u && hi == ((hi >> 7) & 0x01010101u) * 0xAAu) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) out.v[q] = T(0.25) * ((up.v[q] + dn.v[q]) + (lf[q] + rt[q]));
     } else {
@@ -182,10 +212,11 @@ mg_down0v_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restric
     VRegionSmem<T>& S = *reinterpret_cast<VRegionSmem<T>*>(smem_raw);
     const int gi0 = blockIdx.y * FT_Y - VR_H, gj0 = blockIdx.x * FT_X - VR_H;
     vregion_build_op<T>(g, code, gi0, gj0, S);
+    const VLoadSlot LS = vregion_load_slots(g.rows, g.pitch, gi0, gj0);
 
     for (int k = 0; k < g.K; ++k) {
         __syncthreads();
-        vregion_load<T>(r + k * g.plane, g, gi0, gj0, S.rr, S.rb);
+        vregion_load<T>(r + k * g.plane, LS, &S.rr[0][0], &S.rb[0][0]);
         __syncthreads();
         // red: z = r / d
         for (int sl = threadIdx.x; sl < VR_Q * VR_RH; sl += VR_THREADS) {
@@ -242,10 +273,11 @@ mg_up0v_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict_
     const int gi0 = blockIdx.y * FT_Y - VR_H, gj0 = blockIdx.x * FT_X - VR_H;     // both even (multiples of 4)
     const int ntiles = gridDim.x * gridDim.y;
     vregion_build_op<T>(g, code, gi0, gj0, S);
+    const VLoadSlot LS = vregion_load_slots(g.rows, g.pitch, gi0, gj0);
 
     for (int k = 0; k < g.K; ++k) {
         __syncthreads();
-        vregion_load<T>(r + k * g.plane, g, gi0, gj0, S.rr, S.rb);
+        vregion_load<T>(r + k * g.plane, LS, &S.rr[0][0], &S.rb[0][0]);
         if (have_coarse) {
             // coarse correction under the region: rows gi0/2 .. gi0/2 + 20, columns gj0/2 .. gj0/2 + 36 (+ guards),
             // replicated at the far edge of the grid (constant extrapolation of P), clamped at the near edge
