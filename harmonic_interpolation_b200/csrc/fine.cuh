@@ -337,14 +337,15 @@ mg_up0_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict__
 }
 
 // ---- q = A p (+ p.q)   or   r = b - A x (+ r.r) -----------------------------------------------------------
-// One block = the upper or lower 64 x 16 half of a tile, one thread = 4 consecutive columns of one
-// row.  All loads of up to KC channels are issued before any arithmetic and are mutually independent
-// (the rows above / below come straight from L1 / L2), so a warp keeps ~5 KC requests in flight; the
-// block reduction runs once, after the last store.  Partial sums: partial[k * nblocks + block].
+// One block = the upper or lower 64 x 16 half of a tile for KC channels (blockIdx.z selects the
+// channel group; KC = 1 keeps registers low and the number of resident warps high), one thread = 4
+// consecutive columns of one row.  All loads -- flag / code bytes and the five value loads per
+// channel -- are issued together, before any arithmetic, so a block pays ONE memory latency; the
+// block reduction runs once, after the store.  Partial sums: partial[k * nblocks + block].
 // TX is the type of x (and b): T, or double for the master-precision residual of the fp32 mode.
 #define LT_ROWS 16
 template <typename T, typename TX, int MODE, int DOT, int KC, bool PEN>
-__global__ void __launch_bounds__(FT_THREADS, sizeof(TX) == 8 ? 2 : 3)
+__global__ void __launch_bounds__(FT_THREADS, sizeof(TX) == 8 ? 3 : 5)
 lap_tile_kernel(Grid<T> g, const uint8_t* __restrict__ code, const TX* __restrict__ x, const TX* __restrict__ b,
                 T* __restrict__ y, const uint8_t* __restrict__ tile_active, double* __restrict__ partial,
                 const int* __restrict__ done) {
@@ -359,40 +360,21 @@ lap_tile_kernel(Grid<T> g, const uint8_t* __restrict__ code, const TX* __restric
     const int pitch = g.pitch;
     const bool live = i < g.rows && j0 < pitch;
     const long long o = (long long)i * pitch + j0;
-    TX wu[4], wd[4], wl[4], wr[4], dg[4];
     unsigned f4 = 0x01010101u, c4 = 0;
     if (live) {
         f4 = *reinterpret_cast<const unsigned*>(g.flags + o);
         if (!PEN) c4 = *reinterpret_cast<const unsigned*>(code + o);
     }
-    const bool work = (f4 & 0x01010101u) != 0x01010101u;              // some pixel is not hard
-    const bool fast = !PEN && c4 == 0xAAAAAAAAu && (f4 & HG_HS4) == 0; // four regular interior pixels
-    if (live && work && !fast) {
-        unsigned fu4 = 0, fl = 0;
-        if (PEN) {
-            if (i > 0) fu4 = *reinterpret_cast<const unsigned*>(g.flags + o - pitch);
-            if (j0 > 0) fl = g.flags[o - 1];
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const unsigned f = (f4 >> (8 * c)) & 0xffu;
-            T a, bb, cc, dd;
-            if (PEN) flag_weights(g, i, j0 + c, f, (fu4 >> (8 * c)) & 0xffu, c == 0 ? fl : (f4 >> (8 * (c - 1))) & 0xffu, a, bb, cc, dd);
-            else decode((c4 >> (8 * c)) & 0xffu, a, bb, cc, dd);
-            wu[c] = (TX)a; wd[c] = (TX)bb; wl[c] = (TX)cc; wr[c] = (TX)dd;
-            dg[c] = wu[c] + wd[c] + wl[c] + wr[c];
-            if (f & HG_FLAG_SOFT) dg[c] += (TX)soft_w(g, o + c, f);
-        }
-    }
     double acc[KC];
-    for (int k0 = 0; k0 < g.K; k0 += KC) {
+    {
+        const int k0 = blockIdx.z * KC;      // this block's channel group
         V4<TX> cur[KC], up[KC], dn[KC], bv[KC];
         TX xl[KC], xr[KC];
 #pragma unroll
         for (int q = 0; q < KC; ++q) {
             cur[q] = up[q] = dn[q] = bv[q] = zero4<TX>();
             xl[q] = xr[q] = TX(0);
-            if (live && work && k0 + q < g.K) {
+            if (live && k0 + q < g.K) {
                 const TX* xk = x + (k0 + q) * g.plane;
                 cur[q] = ld4(xk + o);
                 if (i > 0) up[q] = ld4(xk + o - pitch);
@@ -400,6 +382,27 @@ lap_tile_kernel(Grid<T> g, const uint8_t* __restrict__ code, const TX* __restric
                 if (j0 > 0) xl[q] = xk[o - 1];
                 if (j0 + 4 < pitch) xr[q] = xk[o + 4];
                 if (MODE == 1 && b) bv[q] = ld4(b + (k0 + q) * g.plane + o);
+            }
+        }
+        // operator of the four pixels (after the value loads have been issued: one memory latency, not two)
+        TX wu[4], wd[4], wl[4], wr[4], dg[4];
+        const bool work = (f4 & 0x01010101u) != 0x01010101u;              // some pixel is not hard
+        const bool fast = !PEN && c4 == 0xAAAAAAAAu && (f4 & HG_HS4) == 0; // four regular interior pixels
+        if (live && work && !fast) {
+            unsigned fu4 = 0, fl = 0;
+            if (PEN) {
+                if (i > 0) fu4 = *reinterpret_cast<const unsigned*>(g.flags + o - pitch);
+                if (j0 > 0) fl = g.flags[o - 1];
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const unsigned f = (f4 >> (8 * c)) & 0xffu;
+                T a, bb, cc, dd;
+                if (PEN) flag_weights(g, i, j0 + c, f, (fu4 >> (8 * c)) & 0xffu, c == 0 ? fl : (f4 >> (8 * (c - 1))) & 0xffu, a, bb, cc, dd);
+                else decode((c4 >> (8 * c)) & 0xffu, a, bb, cc, dd);
+                wu[c] = (TX)a; wd[c] = (TX)bb; wl[c] = (TX)cc; wr[c] = (TX)dd;
+                dg[c] = wu[c] + wd[c] + wl[c] + wr[c];
+                if (f & HG_FLAG_SOFT) dg[c] += (TX)soft_w(g, o + c, f);
             }
         }
 #pragma unroll

@@ -635,13 +635,9 @@ struct Solver : SolverBase {
     void launch_lap_tile_kc(const TX* x, const TX* b, T* y, double* partial, const int* done) {
         const Grid<T> g = grid();
         const dim3 lg = lap_grid();
-        // fp64 operands: two channels per pass keep the loads in registers without spilling
-        switch (std::min(K, sizeof(TX) == 8 ? 2 : 4)) {
-            case 1: lap_tile_kernel<T, TX, MODE, DOT, 1, PEN><<<lg, FT_THREADS, 0, stream>>>(g, d_code, x, b, y, d_tile_active, partial, done); break;
-            case 2: lap_tile_kernel<T, TX, MODE, DOT, 2, PEN><<<lg, FT_THREADS, 0, stream>>>(g, d_code, x, b, y, d_tile_active, partial, done); break;
-            case 3: lap_tile_kernel<T, TX, MODE, DOT, 3, PEN><<<lg, FT_THREADS, 0, stream>>>(g, d_code, x, b, y, d_tile_active, partial, done); break;
-            default: lap_tile_kernel<T, TX, MODE, DOT, 4, PEN><<<lg, FT_THREADS, 0, stream>>>(g, d_code, x, b, y, d_tile_active, partial, done); break;
-        }
+        dim3 lgz = lg;
+        lgz.z = K;      // one channel per block: few registers, many resident warps
+        lap_tile_kernel<T, TX, MODE, DOT, 1, PEN><<<lgz, FT_THREADS, 0, stream>>>(g, d_code, x, b, y, d_tile_active, partial, done);
         ++launches;
     }
     template <typename TX, int MODE, int DOT>
