@@ -338,14 +338,15 @@ mg_up0_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict__
 
 // ---- q = A p (+ p.q)   or   r = b - A x (+ r.r) -----------------------------------------------------------
 // One block = the upper or lower 64 x 16 half of a tile for KC channels (blockIdx.z selects the
-// channel group; KC = 1 keeps registers low and the number of resident warps high), one thread = 4
-// consecutive columns of one row.  All loads -- flag / code bytes and the five value loads per
+// channel group when K > KC), one thread = 4 consecutive columns of one row.  (Measured: one channel
+// per block, 48 registers and 3x the blocks, is 40 % SLOWER -- per-block latency dominates, so a block
+// should carry as many bytes in flight as its registers allow.)  All loads -- flag / code bytes and the five value loads per
 // channel -- are issued together, before any arithmetic, so a block pays ONE memory latency; the
 // block reduction runs once, after the store.  Partial sums: partial[k * nblocks + block].
 // TX is the type of x (and b): T, or double for the master-precision residual of the fp32 mode.
 #define LT_ROWS 16
 template <typename T, typename TX, int MODE, int DOT, int KC, bool PEN>
-__global__ void __launch_bounds__(FT_THREADS, sizeof(TX) == 8 ? 3 : 5)
+__global__ void __launch_bounds__(FT_THREADS, sizeof(TX) == 8 ? 2 : 3)
 lap_tile_kernel(Grid<T> g, const uint8_t* __restrict__ code, const TX* __restrict__ x, const TX* __restrict__ b,
                 T* __restrict__ y, const uint8_t* __restrict__ tile_active, double* __restrict__ partial,
                 const int* __restrict__ done) {

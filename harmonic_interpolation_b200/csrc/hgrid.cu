@@ -635,9 +635,16 @@ struct Solver : SolverBase {
     void launch_lap_tile_kc(const TX* x, const TX* b, T* y, double* partial, const int* done) {
         const Grid<T> g = grid();
         const dim3 lg = lap_grid();
+        // as many channels per block as fit in registers (fp64 operands: two)
+        const int kc = std::min(K, sizeof(TX) == 8 ? 2 : 4);
         dim3 lgz = lg;
-        lgz.z = K;      // one channel per block: few registers, many resident warps
-        lap_tile_kernel<T, TX, MODE, DOT, 1, PEN><<<lgz, FT_THREADS, 0, stream>>>(g, d_code, x, b, y, d_tile_active, partial, done);
+        lgz.z = (K + kc - 1) / kc;
+        switch (kc) {
+            case 1: lap_tile_kernel<T, TX, MODE, DOT, 1, PEN><<<lgz, FT_THREADS, 0, stream>>>(g, d_code, x, b, y, d_tile_active, partial, done); break;
+            case 2: lap_tile_kernel<T, TX, MODE, DOT, 2, PEN><<<lgz, FT_THREADS, 0, stream>>>(g, d_code, x, b, y, d_tile_active, partial, done); break;
+            case 3: lap_tile_kernel<T, TX, MODE, DOT, 3, PEN><<<lgz, FT_THREADS, 0, stream>>>(g, d_code, x, b, y, d_tile_active, partial, done); break;
+            default: lap_tile_kernel<T, TX, MODE, DOT, 4, PEN><<<lgz, FT_THREADS, 0, stream>>>(g, d_code, x, b, y, d_tile_active, partial, done); break;
+        }
         ++launches;
     }
     template <typename TX, int MODE, int DOT>
