@@ -71,6 +71,26 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return s;
 }
 
+// N sums at once (one pair of barriers instead of N); results valid in thread 0.  Blocks of at most
+// 8 warps; `red` holds >= 8 N doubles.
+template <int N>
+__device__ __forceinline__ void block_sum_n(double (&v)[N], double* red) {
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int nw = (blockDim.x * blockDim.y + 31) >> 5;
+#pragma unroll
+    for (int q = 0; q < N; ++q) v[q] = warp_sum(v[q]);
+    __syncthreads();
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int q = 0; q < N; ++q) red[q * 8 + (tid >> 5)] = v[q];
+    }
+    __syncthreads();
+    if (tid < 32) {
+#pragma unroll
+        for (int q = 0; q < N; ++q) v[q] = warp_sum(tid < nw ? red[q * 8 + tid] : 0.0);
+    }
+}
+
 // ---- symmetric Laplacian edge weights (recovery.py:263-299, 309-319) ------------------
 // weight of the edge (i,j)-(i+1,j), given the flag byte of (i,j)
 template <typename T>

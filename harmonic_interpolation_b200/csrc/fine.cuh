@@ -352,7 +352,7 @@ lap_tile_kernel(Grid<T> g, const uint8_t* __restrict__ code, const TX* __restric
                 const int* __restrict__ done) {
     if (done && *done) return;
     if (!tile_active[(blockIdx.y >> 1) * gridDim.x + blockIdx.x]) return;
-    __shared__ double red[32];
+    __shared__ double red[8 * KC];
     const int nblk = gridDim.x * gridDim.y;
     const int blin = blockIdx.y * gridDim.x + blockIdx.x;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -411,6 +411,7 @@ lap_tile_kernel(Grid<T> g, const uint8_t* __restrict__ code, const TX* __restric
             acc[q] = 0.0;
             if (live && k0 + q < g.K) {
                 V4<T> out = zero4<T>();
+                TX part = TX(0);     // the thread's four products in the operand type, then fp64 (conversions are slow)
                 if (work) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -422,18 +423,20 @@ lap_tile_kernel(Grid<T> g, const uint8_t* __restrict__ code, const TX* __restric
                         if (MODE == 1) v = bv[q].v[c] - v;
                         if ((f4 >> (8 * c)) & HG_FLAG_HARD) v = TX(0);
                         out.v[c] = (T)v;
-                        if (DOT == 1) acc[q] += (double)cur[q].v[c] * (double)v;
-                        if (DOT == 2) acc[q] += (double)v * (double)v;
+                        if (DOT == 1) part += cur[q].v[c] * v;
+                        if (DOT == 2) part += v * v;
                     }
                 }
+                acc[q] = (double)part;
                 st4(y + (k0 + q) * g.plane + o, out);
             }
         }
         if (DOT != 0) {
+            block_sum_n<KC>(acc, red);
+            if (threadIdx.x == 0) {
 #pragma unroll
-            for (int q = 0; q < KC; ++q) {
-                const double s = block_sum(acc[q], red);
-                if (threadIdx.x == 0 && k0 + q < g.K) partial[(long long)(k0 + q) * nblk + blin] = s;
+                for (int q = 0; q < KC; ++q)
+                    if (k0 + q < g.K) partial[(long long)(k0 + q) * nblk + blin] = acc[q];
             }
         }
     }

@@ -143,6 +143,7 @@ struct Solver : SolverBase {
     double *d_part0 = nullptr, *d_part1 = nullptr;
     int part_cap = 0;
     CgState* d_state = nullptr;
+    double* d_presum = nullptr;
     unsigned long long* d_counts = nullptr;
     long long launches = 0;
 
@@ -183,7 +184,7 @@ struct Solver : SolverBase {
         cudaFree(d_flags); cudaFree(d_soft); cudaFree(d_dinv);
         cudaFree(d_x); cudaFree(d_b); cudaFree(d_r); cudaFree(d_p); cudaFree(d_q);
         for (auto& p : d_stage) cudaFree(p);
-        cudaFree(d_out); cudaFree(d_part0); cudaFree(d_part1); cudaFree(d_state); cudaFree(d_counts);
+        cudaFree(d_out); cudaFree(d_part0); cudaFree(d_part1); cudaFree(d_state); cudaFree(d_presum); cudaFree(d_counts);
         free_hierarchy();
         cudaFree(d_z);
         if (kRefine) { cudaFree(d_xm); cudaFree(d_bm); }
@@ -201,6 +202,7 @@ struct Solver : SolverBase {
         CU(cudaEventCreate(&ev1));
         CU(cudaMalloc(&d_flags, plane));
         CU(cudaMalloc(&d_state, sizeof(CgState)));
+        CU(cudaMalloc(&d_presum, (size_t)HG_MAXK * PRESUM_BLOCKS * sizeof(double)));
         CU(cudaMalloc(&d_counts, 8 * sizeof(unsigned long long)));
         return HG_OK;
     }
@@ -784,7 +786,15 @@ struct Solver : SolverBase {
 
     // the four scalar stages; with several slabs each is split around an allreduce of the local sums.
     // `part` points at the first owned partial of channel 0, `n` owned partials, `stride` per channel.
+    // many partial sums: add them in chunks first (presum_kernel), the scalar stage adds the chunk sums
+    void presum(const double*& part, int& n, long long& stride, const int* done) {
+        if (n < PRESUM_MIN) return;
+        presum_kernel<<<dim3(PRESUM_BLOCKS, K), 256, 0, stream>>>(done, part, n, stride, d_presum);
+        part = d_presum; n = PRESUM_BLOCKS; stride = PRESUM_BLOCKS;
+        ++launches;
+    }
     int stage_alpha(const double* part, int n, long long stride) {
+        presum(part, n, stride, &d_state->done);
         if (world <= 1) { cg_alpha_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, stride, K, 0); return HG_OK; }
         cg_alpha_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, stride, K, 1);
         HGTRY(allreduce_tmp());
@@ -792,6 +802,7 @@ struct Solver : SolverBase {
         return HG_OK;
     }
     int stage_check(const double* part, int n, long long stride) {
+        presum(part, n, stride, &d_state->done);
         if (world <= 1) { cg_check_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, stride, K, 0); return HG_OK; }
         cg_check_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, stride, K, 1);
         HGTRY(allreduce_tmp());
@@ -799,6 +810,7 @@ struct Solver : SolverBase {
         return HG_OK;
     }
     int stage_beta(const double* part, int n, long long stride, int init) {
+        presum(part, n, stride, &d_state->done);
         if (world <= 1) { cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, stride, K, init, 0); return HG_OK; }
         cg_beta_rz_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, stride, K, init, 1);
         HGTRY(allreduce_tmp());
@@ -806,6 +818,7 @@ struct Solver : SolverBase {
         return HG_OK;
     }
     int stage_outer(const double* part, int n, long long stride, int first, double red2) {
+        presum(part, n, stride, nullptr);
         if (world <= 1) { cg_outer_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, stride, K, first, red2, 0); return HG_OK; }
         cg_outer_kernel<<<1, 1024, 0, stream>>>(d_state, part, n, stride, K, first, red2, 1);
         HGTRY(allreduce_tmp());

@@ -49,6 +49,24 @@ __device__ __forceinline__ double ordered_sum(const double* part, int n, double*
     return block_sum(s, red);
 }
 
+// First level of the ordered sum when there are many partial sums (one per tile of a 16384^2 grid is
+// a quarter of a million): block (c, k) adds a contiguous chunk of channel k's partials; the
+// one-block scalar stage then adds the PRESUM_BLOCKS chunk sums.  Fixed order, deterministic.
+#define PRESUM_BLOCKS 128
+#define PRESUM_MIN 4096
+__global__ void __launch_bounds__(256)
+presum_kernel(const int* __restrict__ done, const double* __restrict__ part, int n, long long stride, double* __restrict__ out) {
+    if (done && *done) return;
+    __shared__ double red[32];
+    const int chunk = (n + gridDim.x - 1) / gridDim.x;
+    const int lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
+    const double* pk = part + (long long)blockIdx.y * stride;
+    double s = 0.0;
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) s += pk[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[blockIdx.y * gridDim.x + blockIdx.x] = s;
+}
+
 // Scalar stages.  `phase` 0: sum the partial sums and finish (single GPU).  Multi-GPU splits a
 // stage around an allreduce of CgState::tmp over the slabs: phase 1 only leaves the local sums
 // in tmp, phase 2 finishes from tmp.
