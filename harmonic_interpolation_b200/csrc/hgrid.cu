@@ -11,6 +11,7 @@
 #include <type_traits>
 #include <vector>
 
+#include "coarse_fused.cuh"
 #include "common.cuh"
 #include "fine.cuh"
 #include "fine_vec.cuh"
@@ -171,7 +172,8 @@ struct Solver : SolverBase {
     uint8_t* d_down_active = nullptr;   // tiles with a free pixel within one pixel (restriction reaches that far)
     uint8_t* d_code = nullptr;          // one byte of edge-weight codes per pixel (fine.cuh)
     double* d_lpart = nullptr;          // partial sums of the stencil kernel (two blocks per tile)
-    bool scalar_legs = getenv("HGRID_SCALAR_LEGS") != nullptr;   // debugging aid: the scalar fused legs of fine.cuh
+    bool scalar_legs = getenv("HGRID_SCALAR_LEGS") != nullptr;
+    bool unfused_coarse = getenv("HGRID_UNFUSED_COARSE") != nullptr;   // debugging aid: one kernel per colour / transfer (mg.cuh)   // debugging aid: the scalar fused legs of fine.cuh
     bool b_is_zero = false;             // no soft / gradient constraints: the right-hand side is identically 0
     bool has_pen = false;
 
@@ -316,10 +318,10 @@ struct Solver : SolverBase {
 
     // ---- multigrid ----------------------------------------------------------------------------
     void free_hierarchy() {
-        for (auto& c : coarse) { cudaFree(c.coef); cudaFree(c.x); cudaFree(c.b); }
-        coarse.clear();
-        for (auto& c : gcoarse) { cudaFree(c.coef); cudaFree(c.x); cudaFree(c.b); }
-        gcoarse.clear();
+        for (auto* lv : {&coarse, &gcoarse}) {
+            for (auto& c : *lv) { cudaFree(c.coef); cudaFree(c.x); cudaFree(c.b); cudaFree(c.code); cudaFree(c.act_up); cudaFree(c.act_down); }
+            lv->clear();
+        }
         cudaFree(d_dense); cudaFree(d_gdense);
         d_dense = d_gdense = nullptr;
     }
@@ -332,6 +334,14 @@ struct Solver : SolverBase {
         L.plane = (long long)L.rows * L.pitch;
         L.K = K;
         L.coef = L.x = L.b = nullptr;
+        L.code = L.act_up = L.act_down = nullptr;
+        L.tiles_x = (L.pitch + CF_TX - 1) / CF_TX;
+        L.tiles_y = (L.rows + CF_TY - 1) / CF_TY;
+        L.has_ref = 0;
+        for (T& v : L.ref) v = T(0);
+        CU(cudaMalloc(&L.code, (size_t)L.plane));
+        CU(cudaMalloc(&L.act_up, (size_t)L.tiles_x * L.tiles_y));
+        CU(cudaMalloc(&L.act_down, (size_t)L.tiles_x * L.tiles_y));
         CU(cudaMalloc(&L.coef, (size_t)L.plane * 9 * sizeof(T)));
         CU(cudaMalloc(&L.x, (size_t)L.plane * K * sizeof(T)));
         CU(cudaMalloc(&L.b, (size_t)L.plane * K * sizeof(T)));
@@ -339,6 +349,94 @@ struct Solver : SolverBase {
         CU(cudaMemsetAsync(L.x, 0, (size_t)L.plane * K * sizeof(T), stream));
         CU(cudaMemsetAsync(L.b, 0, (size_t)L.plane * K * sizeof(T), stream));
         return HG_OK;
+    }
+
+    // Interior stencil of every level: depends on T and the level only.  Taken from the hierarchy of
+    // a 256^2 grid without constraints (centre pixel of each level; the same kernel, so bit-identical
+    // to what the real hierarchy holds wherever the neighbourhood is regular).
+    static constexpr int REF_LEVELS = 5;
+    T ref_stencil[REF_LEVELS + 1][9];
+    bool ref_ready = false;
+    int build_ref_stencils() {
+        if (ref_ready) return HG_OK;
+        const int n = 256;
+        uint8_t* f = nullptr;
+        CU(cudaMalloc(&f, (size_t)n * n));
+        cudaMemsetAsync(f, 0, (size_t)n * n, stream);
+        Grid<T> g;
+        g.rows = g.cols = g.pitch = n; g.plane = (long long)n * n; g.K = 1;
+        g.flags = f; g.soft = nullptr; g.soft_scalar = T(0); g.w_g = T(0);
+        std::vector<Coarse<T>> lv;
+        cudaError_t err = cudaSuccess;
+        for (int l = 1; l <= REF_LEVELS; ++l) {
+            Coarse<T> L;
+            memset(&L, 0, sizeof L);
+            const int m = n >> l;
+            L.rows = L.cols = m; L.pitch = round_up(m, 32); L.plane = (long long)m * L.pitch; L.K = 1;
+            err = cudaMalloc(&L.coef, (size_t)L.plane * 9 * sizeof(T));
+            if (err != cudaSuccess) break;
+            dim3 cg((L.pitch + 127) / 128, L.rows);
+            if (l == 1) galerkin_kernel<T, FineAcc<T>><<<cg, 128, 0, stream>>>(FineAcc<T>{g}, L);
+            else galerkin_kernel<T, CoarseAcc<T>><<<cg, 128, 0, stream>>>(CoarseAcc<T>{lv.back()}, L);
+            lv.push_back(L);
+            for (int c = 0; c < 9; ++c)
+                cudaMemcpyAsync(&ref_stencil[l][c], L.coef + (long long)c * L.plane + (long long)(m / 2) * L.pitch + m / 2, sizeof(T),
+                                cudaMemcpyDeviceToHost, stream);
+        }
+        if (err == cudaSuccess) err = cudaStreamSynchronize(stream);
+        if (err == cudaSuccess) err = cudaGetLastError();
+        for (auto& L : lv) cudaFree(L.coef);
+        cudaFree(f);
+        CU(err);
+        ref_ready = true;
+        return HG_OK;
+    }
+
+    // code bytes and tile activity of a level whose coefficients are final (`level` >= 1)
+    int finish_level(Coarse<T>& L, int level) {
+        L.has_ref = level <= REF_LEVELS;
+        if (L.has_ref)
+            for (int c = 0; c < 9; ++c) L.ref[c] = ref_stencil[level][c];
+        ccode_kernel<T><<<dim3((L.pitch + 255) / 256, L.rows), 256, 0, stream>>>(L);
+        ctile_activity_kernel<<<dim3(L.tiles_x, L.tiles_y), 256, 0, stream>>>(L.code, L.rows, L.cols, L.pitch, 0, L.act_up);
+        ctile_activity_kernel<<<dim3(L.tiles_x, L.tiles_y), 256, 0, stream>>>(L.code, L.rows, L.cols, L.pitch, 1, L.act_down);
+        return HG_OK;
+    }
+
+    template <int KC>
+    int set_fused_attrs() {
+        CU(cudaFuncSetAttribute(cdown_kernel<T, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CFSmem<T, KC, false>)));
+        CU(cudaFuncSetAttribute(cup_kernel<T, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CFSmem<T, KC, true>)));
+        return HG_OK;
+    }
+    template <int KC>
+    void launch_cdown(const Coarse<T>& L, const Coarse<T>& Lc, const int* done) {
+        cdown_kernel<T, KC><<<dim3(L.tiles_x, L.tiles_y, (K + KC - 1) / KC), CF_THREADS, sizeof(CFSmem<T, KC, false>), stream>>>(L, Lc, done);
+    }
+    template <int KC>
+    void launch_cup(const Coarse<T>& L, const Coarse<T>& Lc, const int* done) {
+        cup_kernel<T, KC><<<dim3(L.tiles_x, L.tiles_y, (K + KC - 1) / KC), CF_THREADS, sizeof(CFSmem<T, KC, true>), stream>>>(L, Lc, done);
+    }
+    // fused legs of a 9-point level: pre-smoothing + residual + restriction / prolongation + post-smoothing
+    void coarse_down(const Coarse<T>& L, const Coarse<T>& Lc, const int* done) {
+        if (unfused_coarse) { coarse_pre(L, done); coarse_restrict(L, Lc, done); return; }
+        switch (std::min(K, 4)) {
+            case 1: launch_cdown<1>(L, Lc, done); break;
+            case 2: launch_cdown<2>(L, Lc, done); break;
+            case 3: launch_cdown<3>(L, Lc, done); break;
+            default: launch_cdown<4>(L, Lc, done); break;
+        }
+        ++launches;
+    }
+    void coarse_up(const Coarse<T>& L, const Coarse<T>& Lc, const int* done) {
+        if (unfused_coarse) { coarse_prolong(L, Lc, done); coarse_post(L, done); return; }
+        switch (std::min(K, 4)) {
+            case 1: launch_cup<1>(L, Lc, done); break;
+            case 2: launch_cup<2>(L, Lc, done); break;
+            case 3: launch_cup<3>(L, Lc, done); break;
+            default: launch_cup<4>(L, Lc, done); break;
+        }
+        ++launches;
     }
 
     int build_dense(const Coarse<T>& L, double** out) {
@@ -375,6 +473,7 @@ struct Solver : SolverBase {
         HGTRY(alloc_level(G, chain(global_rows, HG_GATHER_LEVEL), Ll.cols));
         if (G.pitch != Ll.pitch) return fail(HG_ERR_INVALID, "slab mode: pitch mismatch at the gather level");
         HGTRY(gather_level(Ll.coef, Ll.plane, G.coef, G.plane, G.pitch, 9));
+        HGTRY(finish_level(G, HG_GATHER_LEVEL));
         gcoarse.push_back(G);
         int r = G.rows, c = G.cols;
         while ((long long)r * c > 256) {
@@ -383,6 +482,7 @@ struct Solver : SolverBase {
             dim3 cg((L.pitch + 127) / 128, L.rows);
             CoarseAcc<T> ca{gcoarse.back()};
             galerkin_kernel<T, CoarseAcc<T>><<<cg, 128, 0, stream>>>(ca, L);
+            HGTRY(finish_level(L, HG_GATHER_LEVEL + (int)gcoarse.size()));
             gcoarse.push_back(L);
             r = L.rows; c = L.cols;
         }
@@ -427,6 +527,8 @@ struct Solver : SolverBase {
 
     int build_hierarchy() {
         free_hierarchy();
+        HGTRY(build_ref_stencils());
+        HGTRY(set_fused_attrs<1>()); HGTRY(set_fused_attrs<2>()); HGTRY(set_fused_attrs<3>()); HGTRY(set_fused_attrs<4>());
         HGTRY(build_tiles());
         if (!d_z) {
             CU(cudaMalloc(&d_z, (size_t)plane * K * sizeof(T)));
@@ -444,6 +546,7 @@ struct Solver : SolverBase {
                 CoarseAcc<T> ca{coarse.back()};
                 galerkin_kernel<T, CoarseAcc<T>><<<cg, 128, 0, stream>>>(ca, L);
             }
+            HGTRY(finish_level(L, level + 1));
             coarse.push_back(L);
             r = L.rows; c = L.cols;
             ++level;
@@ -488,9 +591,9 @@ struct Solver : SolverBase {
     // V-cycle over levels[from..] of a hierarchy whose first level already holds b (and x = 0)
     void coarse_vcycle(const std::vector<Coarse<T>>& lv, const double* dense, const int* done) {
         const int n = (int)lv.size();
-        for (int l = 0; l + 1 < n; ++l) { coarse_pre(lv[l], done); coarse_restrict(lv[l], lv[l + 1], done); }
+        for (int l = 0; l + 1 < n; ++l) coarse_down(lv[l], lv[l + 1], done);
         coarse_solve(lv[n - 1], dense, done);
-        for (int l = n - 2; l >= 0; --l) { coarse_prolong(lv[l], lv[l + 1], done); coarse_post(lv[l], done); }
+        for (int l = n - 2; l >= 0; --l) coarse_up(lv[l], lv[l + 1], done);
     }
 
     // z = M^-1 r : one V(1,1) cycle from a zero initial guess; also leaves the per-tile partial
@@ -511,8 +614,7 @@ struct Solver : SolverBase {
                 const int Lg = HG_GATHER_LEVEL;
                 for (int l = 0; l + 1 < Lg; ++l) {       // local levels 1 .. Lg-1
                     HGTRY(exchange_level(coarse[l], l + 1, coarse[l].b, K));
-                    coarse_pre(coarse[l], done);
-                    coarse_restrict(coarse[l], coarse[l + 1], done);
+                    coarse_down(coarse[l], coarse[l + 1], done);
                 }
                 // level Lg: gather the owned rows of b, solve replicated, take back the local window of x
                 const Coarse<T>& Ll = coarse[Lg - 1];
@@ -526,8 +628,7 @@ struct Solver : SolverBase {
                                        (size_t)Ll.plane * sizeof(T), cudaMemcpyDeviceToDevice, stream));
                 for (int l = Lg - 2; l >= 0; --l) {
                     if (l + 2 < Lg) HGTRY(exchange_level(coarse[l + 1], l + 2, coarse[l + 1].x, K));
-                    coarse_prolong(coarse[l], coarse[l + 1], done);
-                    coarse_post(coarse[l], done);
+                    coarse_up(coarse[l], coarse[l + 1], done);
                 }
                 HGTRY(exchange_level(coarse[0], 1, coarse[0].x, K));
             }

@@ -29,6 +29,14 @@ struct Coarse {
     T* coef;   // 9 planes
     T* x;      // K planes
     T* b;      // K planes
+    // fused legs (coarse_fused.cuh): code byte per pixel (0 inactive, 1 regular = coefficients equal
+    // `ref`, 2 general), activity of the 64 x 32 tiles (halo 0 / halo 1), the level's interior stencil
+    uint8_t* code;
+    uint8_t* act_up;
+    uint8_t* act_down;
+    int tiles_x, tiles_y;
+    int has_ref;
+    T ref[9];
 };
 
 // ---- transfer weights ---------------------------------------------------------------------
