@@ -1,0 +1,567 @@
+// fine_stream.cuh -- streaming fused V-cycle legs of level 0: registers and warp shuffles only.
+//
+// Same mathematics as the tile legs of fine.cuh / fine_vec.cuh (read the header of fine.cuh first):
+//
+//   down:  z_R = r_R / d,  z_B = (r_B + W z_R) / d,  res_R = W z_B,  b_1 = P^T res,  x_1 = 0
+//   up:    z_R = r_R / d + (P x_1)_R,  z_B = (r_B + W z_R) / d,  z_R = (r_R + W z_B) / d,  r.z
+//
+// but no shared memory and no block barriers.  A WARP owns a column strip: lane l holds the four
+// pixels of columns c0 .. c0+3, c0 = j0 - 4 + 4 l, of the current row, so the warp spans 128 columns
+// of which the middle 120 are its own (4 halo columns on either side); left / right neighbours of a
+// lane's outer pixels come from the adjacent lane by shuffle.  The warp marches DOWN the rows of its
+// chunk (SL_R rows plus 3 rows of run-in and run-out).  Because a red-black sweep only looks one row
+// up and down, the whole leg is a software pipeline over a window of four rows held in registers:
+//
+//   step i:   load r(i+3), code(i+4)                                  [prefetch, see below]
+//             red   pixels of row i      (first update)
+//             black pixels of row i - 1  (needs red of rows i-2, i-1, i)
+//             red   pixels of row i - 2  (residual / second update; needs black of rows i-3, i-2, i-1)
+//             down: every other step the restricted residual of coarse row (i-3)/2 is complete
+//             up:   row i - 2 is final -> one float4 store per lane, r.z accumulated
+//
+// All three stages of a step touch the same two of the lane's four columns (p = parity of i, and
+// p + 2), which keeps the code small: the step is instantiated for even and odd i.
+//
+// Memory behaviour: every load / store is a full 16-byte quad per lane, 512 contiguous bytes per
+// warp and row; r is fetched two rows ahead and the code bytes three rows ahead (the r load is
+// predicated on the quad having a free pixel, so constrained areas cost 1 byte per pixel, not 5).
+// Traffic per pixel and channel: down r (4 B) + code (1 B) + 1/4 (b_1, x_1); up r + z + code + 1/4 x_1.
+// Instruction count: ~10 per pixel and channel against ~85 for the shared-memory legs.
+//
+// Chunks (120 columns x SL_R rows) without a free pixel are skipped (activity bytes at setup; the
+// downward leg uses activity grown by one pixel because restriction reaches that far).
+#pragma once
+#include "fine_vec.cuh"
+
+namespace hg {
+
+#define SL_OUT 120        // columns a warp owns
+#define SL_R 64           // rows per chunk
+#define SL_SPB 2          // strips (warps) per block and channel
+
+// activity of the chunks: 0 = no free pixel within the chunk grown by `halo` (skipped), 1 = simple
+// (every pixel the warp reads is hard or a regular interior pixel -- code 0xAA, no soft weight: the
+// lean code path), 2 = general
+__global__ void sl_activity_kernel(const uint8_t* __restrict__ flags, const uint8_t* __restrict__ code, int rows, int cols, int pitch,
+                                   int halo, int ns, uint8_t* __restrict__ active) {
+    __shared__ int any, general;
+    if (threadIdx.x == 0) any = general = 0;
+    __syncthreads();
+    {
+        const int bi = blockIdx.y * SL_R - halo, bj = blockIdx.x * SL_OUT - halo;
+        const int w = SL_OUT + 2 * halo, h = SL_R + 2 * halo;
+        int mine = 0;
+        for (int e = threadIdx.x; e < w * h; e += blockDim.x) {
+            const int i = bi + e / w, j = bj + e % w;
+            if (i >= 0 && i < rows && j >= 0 && j < cols && !(flags[(long long)i * pitch + j] & HG_FLAG_HARD)) mine = 1;
+        }
+        if (mine) any = 1;
+    }
+    {   // everything the warp may read: rows i0 - 3 .. i0 + SL_R + 8, columns j0 - 4 .. j0 + 123
+        const int bi = blockIdx.y * SL_R - 3, bj = blockIdx.x * SL_OUT - 4;
+        const int w = SL_OUT + 8, h = SL_R + 12;
+        int mine = 0;
+        for (int e = threadIdx.x; e < w * h; e += blockDim.x) {
+            const int i = bi + e / w, j = bj + e % w;
+            if (i >= 0 && i < rows && j >= 0 && j < cols) {
+                const unsigned f = flags[(long long)i * pitch + j], c = code[(long long)i * pitch + j];
+                if (!(f & HG_FLAG_HARD) && (c != 0xAAu || (f & HG_FLAG_SOFT))) mine = 1;
+            }
+        }
+        if (mine) general = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) active[blockIdx.y * ns + blockIdx.x] = (uint8_t)(any ? (general ? 2 : 1) : 0);
+}
+
+template <typename T> __device__ __forceinline__ T sl_up1(T v) { return __shfl_up_sync(HG_FULL, v, 1); }
+template <typename T> __device__ __forceinline__ T sl_dn1(T v) { return __shfl_down_sync(HG_FULL, v, 1); }
+
+// weighted sum of the four neighbours of a pixel with code byte cb
+template <typename T>
+__device__ __forceinline__ T sl_nsum(unsigned cb, T up, T dn, T lf, T rt) {
+    // (a code of 0 -- hard, or isolated -- also takes this branch: its result is masked by dinv = 0 or
+    // multiplies neighbours that do not exist; this keeps warps with hard pixels from diverging)
+    if (cb == 0xAAu || cb == 0u) return cb ? T(0.25) * ((up + dn) + (lf + rt)) : T(0);
+    T wu, wd, wl, wr;
+    decode(cb, wu, wd, wl, wr);
+    return wu * up + wd * dn + wl * lf + wr * rt;
+}
+
+// what a lane knows about the operator on its quad of one row
+template <bool SOFT> struct SlRowOp {
+    unsigned cw;      // four code bytes (0 outside the grid)
+    unsigned fw;      // four flag bytes (SOFT only)
+};
+
+template <typename T, bool SOFT>
+struct SlCtx {
+    Grid<T> g;
+    const uint8_t* code;
+    int c0;           // first column of the lane's quad
+    bool colin;       // the quad lies inside the pitch
+    __device__ __forceinline__ SlRowOp<SOFT> load_op(int i) const {
+        SlRowOp<SOFT> o;
+        o.cw = 0u; o.fw = 0x01010101u;
+        if (colin && i >= 0 && i < g.rows) {
+            const long long off = (long long)i * g.pitch + c0;
+            o.cw = *reinterpret_cast<const unsigned*>(code + off);
+            if (SOFT) o.fw = *reinterpret_cast<const unsigned*>(g.flags + off);
+        }
+        return o;
+    }
+    // does the quad hold a pixel that is not hard (so that r can be non-zero there)?
+    __device__ __forceinline__ bool any_free(const SlRowOp<SOFT>& o) const {
+        return SOFT ? (o.fw & 0x01010101u) != 0x01010101u : o.cw != 0u;
+    }
+    __device__ __forceinline__ V4<T> load_row(const T* __restrict__ v, int i, const SlRowOp<SOFT>& o) const {
+        if (any_free(o)) return ld4(v + (long long)i * g.pitch + c0);
+        return zero4<T>();
+    }
+    __device__ __forceinline__ T dinv(const SlRowOp<SOFT>& o, int i, int p) const {
+        const unsigned cb = (o.cw >> (8 * p)) & 0xffu;
+        if (!SOFT) {
+            if (cb == 0xAAu) return T(1);
+            if (cb == 0u) return T(0);
+            return T(8) / T((cb & 3u) + ((cb >> 2) & 3u) + ((cb >> 4) & 3u) + ((cb >> 6) & 3u));
+        }
+        return dinv_of(g, cb, (o.fw >> (8 * p)) & 0xffu, (long long)i * g.pitch + c0 + p);
+    }
+};
+
+// Gauss-Seidel update of the two pixels p = PAR, PAR + 2 of row `row` (quad zc, right-hand side rc),
+// given the quads of the rows above (zu) and below (zd):  zc[p] = (rc[p] + W z) * dinv.
+// RESID: zc[p] = W z where the pixel is free, 0 elsewhere (the residual after a sweep from zero).
+template <typename T, bool SOFT, int PAR, bool RESID>
+__device__ __forceinline__ void sl_update(const SlCtx<T, SOFT>& cx, const SlRowOp<SOFT>& op, int row, V4<T>& zc, const V4<T>& zsrc,
+                                          const V4<T>& rc, const V4<T>& zu, const V4<T>& zd) {
+    // neighbours along the row come from zsrc (the same row: values of the other colour)
+    const T fromL = sl_up1(zsrc.v[3]), fromR = sl_dn1(zsrc.v[0]);
+    const T lfA = PAR == 0 ? fromL : zsrc.v[0], rtA = PAR == 0 ? zsrc.v[1] : zsrc.v[2];
+    const T lfB = PAR == 0 ? zsrc.v[1] : zsrc.v[2], rtB = PAR == 0 ? zsrc.v[3] : fromR;
+    const int pa = PAR, pb = PAR + 2;
+    const unsigned cbA = (op.cw >> (8 * pa)) & 0xffu, cbB = (op.cw >> (8 * pb)) & 0xffu;
+    const T diA = cx.dinv(op, row, pa), diB = cx.dinv(op, row, pb);
+    const T nsA = sl_nsum<T>(cbA, zu.v[pa], zd.v[pa], lfA, rtA), nsB = sl_nsum<T>(cbB, zu.v[pb], zd.v[pb], lfB, rtB);
+    if (RESID) {
+        zc.v[pa] = diA != T(0) ? nsA : T(0);
+        zc.v[pb] = diB != T(0) ? nsB : T(0);
+    } else {
+        zc.v[pa] = (rc.v[pa] + nsA) * diA;
+        zc.v[pb] = (rc.v[pb] + nsB) * diB;
+    }
+}
+
+// ---- downward leg -------------------------------------------------------------------------------------
+template <typename T, bool SOFT>
+struct SlDown {
+    SlCtx<T, SOFT> cx;
+    const T* rk;                 // this channel's plane of r
+    Coarse<T> cl;
+    T* bk; T* xk;                // this channel's planes of the next level
+    int i0, lane;
+    bool owner;                  // lanes 1..30 own their columns
+    T wjm[2], wjp[2];            // restriction weights of the lane's two coarse columns
+    // pipeline registers
+    V4<T> z0, z1, z2, z3, r1, s0, s1, s2;
+    SlRowOp<SOFT> o0, o1, o2;
+    V4<T> rq0, rq1;              // r of rows i+1, i+2
+    SlRowOp<SOFT> q0, q1, q2;    // operator of rows i+1, i+2, i+3
+
+    template <int PAR>
+    __device__ __forceinline__ void step(int i, const V4<T>& rc) {
+        const int pa = PAR, pb = PAR + 2;
+        // red pixels of row i
+        z0 = zero4<T>();
+        z0.v[pa] = rc.v[pa] * cx.dinv(o0, i, pa);
+        z0.v[pb] = rc.v[pb] * cx.dinv(o0, i, pb);
+        // black pixels of row i - 1
+        sl_update<T, SOFT, PAR, false>(cx, o1, i - 1, z1, z1, r1, z2, z0);
+        // residual at the red pixels of row i - 2
+        s0 = zero4<T>();
+        sl_update<T, SOFT, PAR, true>(cx, o2, i - 2, s0, z2, r1, z3, z1);
+        if (PAR == 1) {
+            // coarse row I sits on row i - 3 (even): centre s1, diagonals in s2 (above) and s0 (below)
+            const int ic = i - 3, I = ic >> 1;
+            const T upL = sl_up1(s2.v[3]), dnL = sl_up1(s0.v[3]);
+            if (ic >= i0 && ic < i0 + SL_R && I < cl.rows && owner && cx.colin) {
+                const int Ja = cx.c0 >> 1;
+                if (Ja < cl.cols) {
+                    const T wim = (T)w1d(-1, I, cx.g.rows, cl.rows), wip = (T)w1d(1, I, cx.g.rows, cl.rows);
+                    const T va = s1.v[0] + wim * (wjm[0] * upL + wjp[0] * s2.v[1]) + wip * (wjm[0] * dnL + wjp[0] * s0.v[1]);
+                    T vb = s1.v[2] + wim * (wjm[1] * s2.v[1] + wjp[1] * s2.v[3]) + wip * (wjm[1] * s0.v[1] + wjp[1] * s0.v[3]);
+                    if (Ja + 1 >= cl.cols) vb = T(0);
+                    const long long oc = (long long)I * cl.pitch + Ja;
+                    sts2(bk + oc, va, vb);
+                    sts2(xk + oc, T(0), T(0));
+                }
+            }
+        }
+    }
+
+    __device__ __forceinline__ void run() {
+        const int ibeg = i0 - 3;
+        z1 = z2 = z3 = r1 = s1 = s2 = zero4<T>();
+        o1.cw = o2.cw = 0u; o1.fw = o2.fw = 0x01010101u;
+        o0 = cx.load_op(ibeg); q0 = cx.load_op(ibeg + 1); q1 = cx.load_op(ibeg + 2); q2 = cx.load_op(ibeg + 3);
+        V4<T> rc = cx.load_row(rk, ibeg, o0);
+        rq0 = cx.load_row(rk, ibeg + 1, q0);
+        rq1 = cx.load_row(rk, ibeg + 2, q1);
+#pragma unroll 1
+        for (int i = ibeg; i < i0 + SL_R + 3; i += 2) {
+            adv<1>(i, rc);          // ibeg is odd
+            adv<0>(i + 1, rc);
+        }
+    }
+    template <int PAR>
+    __device__ __forceinline__ void adv(int i, V4<T>& rc) {
+        const V4<T> rnew = cx.load_row(rk, i + 3, q2);
+        const SlRowOp<SOFT> onew = cx.load_op(i + 4);
+        step<PAR>(i, rc);
+        z3 = z2; z2 = z1; z1 = z0; r1 = rc; s2 = s1; s1 = s0; o2 = o1; o1 = o0;
+        rc = rq0; rq0 = rq1; rq1 = rnew; o0 = q0; q0 = q1; q1 = q2; q2 = onew;
+    }
+};
+
+
+// ---- lean paths for simple chunks ----------------------------------------------------------------------
+// All weights are 1/4 and the inverse diagonal is 1 at free pixels (code byte != 0), 0 elsewhere.  The
+// row window lives in rings of eight slots (row i <-> slot i & 7) and the loop is unrolled eight
+// steps, so every slot index is a compile-time constant and the rotation costs no register moves.
+template <typename T>
+struct SlLean {
+    const uint8_t* code;
+    const T* rk;
+    int rows, pitch, c0, i0;
+    bool colin, owner;
+    V4<T> Z[8], R[8];
+    unsigned M[8];
+    __device__ __forceinline__ unsigned load_code(int i) const {
+        return (colin && i >= 0 && i < rows) ? *reinterpret_cast<const unsigned*>(code + (long long)i * pitch + c0) : 0u;
+    }
+    __device__ __forceinline__ V4<T> load_r(int i, unsigned m) const {
+        if (m) return ld4(rk + (long long)i * pitch + c0);
+        return zero4<T>();
+    }
+    __device__ __forceinline__ void init(int ibeg, int slot0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { Z[q] = zero4<T>(); R[q] = zero4<T>(); M[q] = 0u; }
+        // rows ibeg .. ibeg + 3 of the codes, ibeg .. ibeg + 2 of r  (slot0 = ibeg & 7, a compile-time fact of the caller)
+        M[slot0 & 7] = load_code(ibeg); M[(slot0 + 1) & 7] = load_code(ibeg + 1);
+        M[(slot0 + 2) & 7] = load_code(ibeg + 2); M[(slot0 + 3) & 7] = load_code(ibeg + 3);
+        R[slot0 & 7] = load_r(ibeg, M[slot0 & 7]);
+        R[(slot0 + 1) & 7] = load_r(ibeg + 1, M[(slot0 + 1) & 7]);
+        R[(slot0 + 2) & 7] = load_r(ibeg + 2, M[(slot0 + 2) & 7]);
+    }
+    template <int C> __device__ __forceinline__ void prefetch(int i) {
+        M[(C + 4) & 7] = load_code(i + 4);
+        R[(C + 3) & 7] = load_r(i + 3, M[(C + 3) & 7]);
+    }
+    // red pixels of row i (slot C): z = r where free
+    template <int C, int PAR> __device__ __forceinline__ void red_first(const T addA, const T addB) {
+        const unsigned m = M[C];
+        Z[C] = zero4<T>();
+        Z[C].v[PAR] = (m & (0xffu << (8 * PAR))) ? R[C].v[PAR] + addA : T(0);
+        Z[C].v[PAR + 2] = (m & (0xffu << (8 * (PAR + 2)))) ? R[C].v[PAR + 2] + addB : T(0);
+    }
+    // 1/4 of the four neighbours of the pixels PAR, PAR + 2 of slot C (rows above / below: slots CU, CD)
+    template <int C, int CU, int CD, int PAR> __device__ __forceinline__ void nsum(T& nA, T& nB) const {
+        T lfA, rtA, lfB, rtB;
+        if (PAR == 0) { lfA = sl_up1(Z[C].v[3]); rtA = Z[C].v[1]; lfB = Z[C].v[1]; rtB = Z[C].v[3]; }
+        else          { lfA = Z[C].v[0]; rtA = Z[C].v[2]; lfB = Z[C].v[2]; rtB = sl_dn1(Z[C].v[0]); }
+        nA = T(0.25) * ((Z[CU].v[PAR] + Z[CD].v[PAR]) + (lfA + rtA));
+        nB = T(0.25) * ((Z[CU].v[PAR + 2] + Z[CD].v[PAR + 2]) + (lfB + rtB));
+    }
+    // Gauss-Seidel update of the pixels PAR, PAR + 2 of slot C
+    template <int C, int CU, int CD, int PAR> __device__ __forceinline__ void update() {
+        T nA, nB;
+        nsum<C, CU, CD, PAR>(nA, nB);
+        const unsigned m = M[C];
+        Z[C].v[PAR] = (m & (0xffu << (8 * PAR))) ? R[C].v[PAR] + nA : T(0);
+        Z[C].v[PAR + 2] = (m & (0xffu << (8 * (PAR + 2)))) ? R[C].v[PAR + 2] + nB : T(0);
+    }
+};
+
+template <typename T>
+struct SlLeanDown : SlLean<T> {
+    using B = SlLean<T>;
+    T* bk; T* xk;
+    int grows, crows, ccols, cpitch;
+    T wjm[2], wjp[2];
+    V4<T> S[8];
+
+    template <int U> __device__ __forceinline__ void step(int ib) {     // ib = i0 - 3 (mod 8: 5)
+        constexpr int C = (5 + U) & 7, C1 = (C + 7) & 7, C2 = (C + 6) & 7, C3 = (C + 5) & 7, C4 = (C + 4) & 7;
+        constexpr int PAR = (5 + U) & 1;
+        const int i = ib + U;
+        B::template prefetch<C>(i);
+        B::template red_first<C, PAR>(T(0), T(0));
+        B::template update<C1, C2, C, PAR>();                  // black pixels of row i - 1
+        {   // residual at the red pixels of row i - 2
+            T nA, nB;
+            B::template nsum<C2, C3, C1, PAR>(nA, nB);
+            const unsigned m = B::M[C2];
+            S[C2] = zero4<T>();
+            S[C2].v[PAR] = (m & (0xffu << (8 * PAR))) ? nA : T(0);
+            S[C2].v[PAR + 2] = (m & (0xffu << (8 * (PAR + 2)))) ? nB : T(0);
+        }
+        if (PAR == 1) {
+            const int ic = i - 3, I = ic >> 1;
+            const T upL = sl_up1(S[C4].v[3]), dnL = sl_up1(S[C2].v[3]);
+            if (ic >= B::i0 && ic < B::i0 + SL_R && I < crows && B::owner && B::colin) {
+                const int Ja = B::c0 >> 1;
+                if (Ja < ccols) {
+                    const T wim = (T)w1d(-1, I, grows, crows), wip = (T)w1d(1, I, grows, crows);
+                    const T va = S[C3].v[0] + wim * (wjm[0] * upL + wjp[0] * S[C4].v[1]) + wip * (wjm[0] * dnL + wjp[0] * S[C2].v[1]);
+                    T vb = S[C3].v[2] + wim * (wjm[1] * S[C4].v[1] + wjp[1] * S[C4].v[3]) + wip * (wjm[1] * S[C2].v[1] + wjp[1] * S[C2].v[3]);
+                    if (Ja + 1 >= ccols) vb = T(0);
+                    const long long oc = (long long)I * cpitch + Ja;
+                    sts2(bk + oc, va, vb);
+                    sts2(xk + oc, T(0), T(0));
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void run() {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) S[q] = zero4<T>();
+        B::init(B::i0 - 3, 5);
+#pragma unroll 1
+        for (int ib = B::i0 - 3; ib < B::i0 + SL_R + 3; ib += 8) {
+            step<0>(ib); step<1>(ib); step<2>(ib); step<3>(ib); step<4>(ib); step<5>(ib); step<6>(ib); step<7>(ib);
+        }
+    }
+};
+
+template <typename T>
+struct SlLeanUp : SlLean<T> {
+    using B = SlLean<T>;
+    T* zk;
+    const T* ek;
+    int crows, ccols, cpitch;
+    double acc;
+    T E[4][3];        // coarse rows, slot I & 3: the lane's two columns and the next lane's first
+
+    template <int SLOT> __device__ __forceinline__ void load_e(int I) {
+        T a = T(0), b = T(0);
+        if (ek) {
+            const int Ic = min(max(I, 0), crows - 1);
+            const int J0 = min(max(B::c0 >> 1, 0), ccols - 1), J1 = min(max((B::c0 >> 1) + 1, 0), ccols - 1);
+            const T* row = ek + (long long)Ic * cpitch;
+            a = row[J0]; b = row[J1];
+        }
+        E[SLOT][0] = a; E[SLOT][1] = b;
+        E[SLOT][2] = sl_dn1(a);
+    }
+    template <int U> __device__ __forceinline__ void step(int ib) {     // ib = i0 - 2 (mod 8: 6)
+        constexpr int C = (6 + U) & 7, C1 = (C + 7) & 7, C2 = (C + 6) & 7, C3 = (C + 5) & 7;
+        constexpr int PAR = U & 1;
+        constexpr int EA = (3 + U / 2) & 3, EB = (EA + 1) & 3, EN = (EA + 2) & 3;      // (ib >> 1) & 3 == 3
+        const int i = ib + U;
+        B::template prefetch<C>(i);
+        if (PAR == 0) {
+            load_e<EN>((i >> 1) + 2);
+            B::template red_first<C, 0>(E[EA][0], E[EA][1]);
+        } else {
+            B::template red_first<C, 1>(T(0.25) * ((E[EA][0] + E[EA][1]) + (E[EB][0] + E[EB][1])),
+                                        T(0.25) * ((E[EA][1] + E[EA][2]) + (E[EB][1] + E[EB][2])));
+        }
+        B::template update<C1, C2, C, PAR>();                  // black pixels of row i - 1
+        B::template update<C2, C3, C1, PAR>();                 // red pixels of row i - 2 again
+        const int io = i - 2;
+        if (io >= B::i0 && io < B::i0 + SL_R && B::owner && B::M[C2]) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc += (double)(B::Z[C2].v[p] * B::R[C2].v[p]);
+            st4(zk + (long long)io * B::pitch + B::c0, B::Z[C2]);
+        }
+    }
+    __device__ __forceinline__ void run() {
+        acc = 0.0;
+        B::init(B::i0 - 2, 6);
+        load_e<3>((B::i0 - 2) >> 1);
+        load_e<0>(((B::i0 - 2) >> 1) + 1);
+#pragma unroll 1
+        for (int ib = B::i0 - 2; ib < B::i0 + SL_R + 2; ib += 8) {
+            step<0>(ib); step<1>(ib); step<2>(ib); step<3>(ib); step<4>(ib); step<5>(ib); step<6>(ib); step<7>(ib);
+        }
+    }
+};
+
+template <typename T, bool SOFT>
+__global__ void __launch_bounds__(32 * SL_SPB * 4)
+sl_down_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict__ r, Coarse<T> cl, const uint8_t* __restrict__ active,
+               int ns, const int* __restrict__ done) {
+    if (done && *done) return;
+    const int s = blockIdx.x * SL_SPB + threadIdx.y, t = blockIdx.y, k = blockIdx.z * blockDim.z + threadIdx.z;
+    if (s >= ns || k >= g.K) return;
+    const unsigned act = active[t * ns + s];
+    if (!act) return;
+    if (act == 1u) {
+        SlLeanDown<T> f;
+        f.code = code; f.rk = r + k * g.plane;
+        f.rows = g.rows; f.pitch = g.pitch; f.i0 = t * SL_R;
+        f.c0 = s * SL_OUT - 4 + 4 * (int)threadIdx.x;
+        f.colin = f.c0 >= 0 && f.c0 < g.pitch;
+        f.owner = threadIdx.x >= 1 && threadIdx.x <= 30;
+        f.bk = cl.b + k * cl.plane; f.xk = cl.x + k * cl.plane;
+        f.grows = g.rows; f.crows = cl.rows; f.ccols = cl.cols; f.cpitch = cl.pitch;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int J = (f.c0 >> 1) + q;
+            f.wjm[q] = (T)w1d(-1, J, g.cols, cl.cols);
+            f.wjp[q] = (T)w1d(1, J, g.cols, cl.cols);
+        }
+        f.run();
+        return;
+    }
+    SlDown<T, SOFT> d;
+    d.lane = threadIdx.x;
+    d.cx.g = g; d.cx.code = code;
+    d.cx.c0 = s * SL_OUT - 4 + 4 * d.lane;
+    d.cx.colin = d.cx.c0 >= 0 && d.cx.c0 < g.pitch;
+    d.owner = d.lane >= 1 && d.lane <= 30;
+    d.rk = r + k * g.plane;
+    d.cl = cl;
+    d.bk = cl.b + k * cl.plane; d.xk = cl.x + k * cl.plane;
+    d.i0 = t * SL_R;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int J = (d.cx.c0 >> 1) + q;
+        d.wjm[q] = (T)w1d(-1, J, g.cols, cl.cols);
+        d.wjp[q] = (T)w1d(1, J, g.cols, cl.cols);
+    }
+    d.run();
+}
+
+// ---- upward leg -----------------------------------------------------------------------------------------
+template <typename T, bool SOFT>
+struct SlUp {
+    SlCtx<T, SOFT> cx;
+    const T* rk; T* zk;
+    const T* ek;                 // this channel's plane of the next level's x (nullptr: no coarse level)
+    int crows, ccols, cpitch;
+    int i0, lane;
+    bool owner;
+    double acc;
+    V4<T> z0, z1, z2, z3, r1, r2;
+    SlRowOp<SOFT> o0, o1, o2;
+    V4<T> rq0, rq1;
+    SlRowOp<SOFT> q0, q1, q2;
+    T ea[3], eb[3];              // coarse correction under the quad: rows floor(i/2) and floor(i/2) + 1, columns c0/2 .. c0/2 + 2
+
+    // coarse row I (clamped: replicated at the far edge, as P extrapolates by a constant), the lane's two columns
+    __device__ __forceinline__ void load_e(int I, T (&e)[3]) const {
+        e[0] = e[1] = T(0);
+        if (ek) {     // also for lanes beyond the last column: their clamped value is the neighbour's replicated one
+            const int Ic = min(max(I, 0), crows - 1);
+            const int J0 = min(max(cx.c0 >> 1, 0), ccols - 1), J1 = min(max((cx.c0 >> 1) + 1, 0), ccols - 1);
+            const T* row = ek + (long long)Ic * cpitch;
+            e[0] = row[J0]; e[1] = row[J1];
+        }
+    }
+
+    template <int PAR>
+    __device__ __forceinline__ void step(int i, const V4<T>& rc) {
+        const int pa = PAR, pb = PAR + 2;
+        // red pixels of row i: r / d + (P e)
+        {
+            const T dA = cx.dinv(o0, i, pa), dB = cx.dinv(o0, i, pb);
+            T zA = rc.v[pa] * dA, zB = rc.v[pb] * dB;
+            if (PAR == 0) {          // even row, even columns: injection
+                if (dA != T(0)) zA += ea[0];
+                if (dB != T(0)) zB += ea[1];
+            } else {                 // odd row, odd columns: mean of four
+                if (dA != T(0)) zA += T(0.25) * ((ea[0] + ea[1]) + (eb[0] + eb[1]));
+                if (dB != T(0)) zB += T(0.25) * ((ea[1] + ea[2]) + (eb[1] + eb[2]));
+            }
+            z0 = zero4<T>();
+            z0.v[pa] = zA; z0.v[pb] = zB;
+        }
+        // black pixels of row i - 1
+        sl_update<T, SOFT, PAR, false>(cx, o1, i - 1, z1, z1, r1, z2, z0);
+        // red pixels of row i - 2 again
+        sl_update<T, SOFT, PAR, false>(cx, o2, i - 2, z2, z2, r2, z3, z1);
+        // row i - 2 is final
+        const int io = i - 2;
+        if (io >= i0 && io < i0 + SL_R && io < cx.g.rows && owner && cx.colin) {
+            if (cx.any_free(o2)) {
+#pragma unroll
+                for (int p = 0; p < 4; ++p) acc += (double)(z2.v[p] * r2.v[p]);
+                st4(zk + (long long)io * cx.g.pitch + cx.c0, z2);
+            }
+        }
+    }
+
+    template <int PAR>
+    __device__ __forceinline__ void adv(int i, V4<T>& rc) {
+        const V4<T> rnew = cx.load_row(rk, i + 3, q2);
+        const SlRowOp<SOFT> onew = cx.load_op(i + 4);
+        if (PAR == 0) {
+            // a new pair of coarse rows: floor(i/2) (already held in eb) and floor(i/2) + 1
+            ea[0] = eb[0]; ea[1] = eb[1]; ea[2] = eb[2];
+            load_e((i >> 1) + 1, eb);
+            eb[2] = sl_dn1(eb[0]);
+        }
+        step<PAR>(i, rc);
+        z3 = z2; z2 = z1; z1 = z0; r2 = r1; r1 = rc; o2 = o1; o1 = o0;
+        rc = rq0; rq0 = rq1; rq1 = rnew; o0 = q0; q0 = q1; q1 = q2; q2 = onew;
+    }
+
+    __device__ __forceinline__ void run() {
+        const int ibeg = i0 - 2;     // even
+        z1 = z2 = z3 = r1 = r2 = zero4<T>();
+        o1.cw = o2.cw = 0u; o1.fw = o2.fw = 0x01010101u;
+        o0 = cx.load_op(ibeg); q0 = cx.load_op(ibeg + 1); q1 = cx.load_op(ibeg + 2); q2 = cx.load_op(ibeg + 3);
+        V4<T> rc = cx.load_row(rk, ibeg, o0);
+        rq0 = cx.load_row(rk, ibeg + 1, q0);
+        rq1 = cx.load_row(rk, ibeg + 2, q1);
+        load_e(ibeg >> 1, eb);
+        eb[2] = sl_dn1(eb[0]);
+        acc = 0.0;
+#pragma unroll 1
+        for (int i = ibeg; i < i0 + SL_R + 2; i += 2) {
+            adv<0>(i, rc);
+            adv<1>(i + 1, rc);
+        }
+    }
+};
+
+template <typename T, bool SOFT>
+__global__ void __launch_bounds__(32 * SL_SPB * 4)
+sl_up_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict__ r, T* __restrict__ z, Coarse<T> cl, int have_coarse,
+             const uint8_t* __restrict__ active, int ns, double* __restrict__ part_rz, const int* __restrict__ done) {
+    if (done && *done) return;
+    const int s = blockIdx.x * SL_SPB + threadIdx.y, t = blockIdx.y, k = blockIdx.z * blockDim.z + threadIdx.z;
+    if (s >= ns || k >= g.K) return;
+    const unsigned act = active[t * ns + s];
+    if (!act) return;
+    if (act == 1u) {
+        SlLeanUp<T> f;
+        f.code = code; f.rk = r + k * g.plane; f.zk = z + k * g.plane;
+        f.rows = g.rows; f.pitch = g.pitch; f.i0 = t * SL_R;
+        f.c0 = s * SL_OUT - 4 + 4 * (int)threadIdx.x;
+        f.colin = f.c0 >= 0 && f.c0 < g.pitch;
+        f.owner = threadIdx.x >= 1 && threadIdx.x <= 30;
+        f.ek = have_coarse ? cl.x + k * cl.plane : nullptr;
+        f.crows = cl.rows; f.ccols = cl.cols; f.cpitch = cl.pitch;
+        f.run();
+        const double sdot = warp_sum(f.acc);
+        if (threadIdx.x == 0) part_rz[(long long)k * (ns * gridDim.y) + (long long)t * ns + s] = sdot;
+        return;
+    }
+    SlUp<T, SOFT> u;
+    u.lane = threadIdx.x;
+    u.cx.g = g; u.cx.code = code;
+    u.cx.c0 = s * SL_OUT - 4 + 4 * u.lane;
+    u.cx.colin = u.cx.c0 >= 0 && u.cx.c0 < g.pitch;
+    u.owner = u.lane >= 1 && u.lane <= 30;
+    u.rk = r + k * g.plane; u.zk = z + k * g.plane;
+    u.ek = have_coarse ? cl.x + k * cl.plane : nullptr;
+    u.crows = cl.rows; u.ccols = cl.cols; u.cpitch = cl.pitch;
+    u.i0 = t * SL_R;
+    u.run();
+    const double sdot = warp_sum(u.acc);
+    if (u.lane == 0) part_rz[(long long)k * (ns * gridDim.y) + (long long)t * ns + s] = sdot;
+}
+
+}  // namespace hg

@@ -14,6 +14,7 @@
 #include "coarse_fused.cuh"
 #include "common.cuh"
 #include "fine.cuh"
+#include "fine_stream.cuh"
 #include "fine_vec.cuh"
 #include "mg.cuh"
 #include "pcg.cuh"
@@ -172,6 +173,11 @@ struct Solver : SolverBase {
     uint8_t* d_down_active = nullptr;   // tiles with a free pixel within one pixel (restriction reaches that far)
     uint8_t* d_code = nullptr;          // one byte of edge-weight codes per pixel (fine.cuh)
     double* d_lpart = nullptr;          // partial sums of the stencil kernel (two blocks per tile)
+    // streaming legs (fine_stream.cuh): chunk activity (halo 0 / halo 1) and per-chunk partial sums of r.z
+    uint8_t *d_sl_up = nullptr, *d_sl_down = nullptr;
+    double* d_spart = nullptr;
+    int sl_ns = 0, sl_nt = 0;
+    bool tile_legs = getenv("HGRID_TILE_LEGS") != nullptr;       // debugging aid: the shared-memory legs of fine_vec.cuh
     bool scalar_legs = getenv("HGRID_SCALAR_LEGS") != nullptr;
     bool unfused_coarse = getenv("HGRID_UNFUSED_COARSE") != nullptr;   // debugging aid: one kernel per colour / transfer (mg.cuh)   // debugging aid: the scalar fused legs of fine.cuh
     bool b_is_zero = false;             // no soft / gradient constraints: the right-hand side is identically 0
@@ -192,6 +198,7 @@ struct Solver : SolverBase {
         if (kRefine) { cudaFree(d_xm); cudaFree(d_bm); }
         cudaFree(d_tile_active); cudaFree(d_tpart0); cudaFree(d_tpart1);
         cudaFree(d_down_active); cudaFree(d_code); cudaFree(d_lpart);
+        cudaFree(d_sl_up); cudaFree(d_sl_down); cudaFree(d_spart);
         if (comm && g_nccl.ok) g_nccl.CommDestroy(comm);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -516,6 +523,16 @@ struct Solver : SolverBase {
         tile_activity_kernel<<<tile_grid(), 256, 0, stream>>>(d_flags, rows, cols, pitch, 0, d_tile_active);
         tile_activity_kernel<<<tile_grid(), 256, 0, stream>>>(d_flags, rows, cols, pitch, 1, d_down_active);
         opcode_kernel<T><<<dim3((pitch + 255) / 256, rows), 256, 0, stream>>>(grid(), d_code);
+        sl_ns = (pitch + SL_OUT - 1) / SL_OUT;
+        sl_nt = (rows + SL_R - 1) / SL_R;
+        cudaFree(d_sl_up); cudaFree(d_sl_down); cudaFree(d_spart);
+        d_sl_up = d_sl_down = nullptr; d_spart = nullptr;
+        CU(cudaMalloc(&d_sl_up, (size_t)sl_ns * sl_nt));
+        CU(cudaMalloc(&d_sl_down, (size_t)sl_ns * sl_nt));
+        CU(cudaMalloc(&d_spart, (size_t)sl_ns * sl_nt * K * sizeof(double)));
+        CU(cudaMemsetAsync(d_spart, 0, (size_t)sl_ns * sl_nt * K * sizeof(double), stream));
+        sl_activity_kernel<<<dim3(sl_ns, sl_nt), 256, 0, stream>>>(d_flags, d_code, rows, cols, pitch, 0, sl_ns, d_sl_up);
+        sl_activity_kernel<<<dim3(sl_ns, sl_nt), 256, 0, stream>>>(d_flags, d_code, rows, cols, pitch, 1, sl_ns, d_sl_down);
         CU(cudaFuncSetAttribute(mg_down0_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, DOWN_H, false>)));
         CU(cudaFuncSetAttribute(mg_down0_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, DOWN_H, true>)));
         CU(cudaFuncSetAttribute(mg_up0_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, UP_H, false>)));
@@ -604,7 +621,8 @@ struct Solver : SolverBase {
         const int nl = (int)coarse.size();
         if (nl > 0) {
             if (world > 1) HGTRY(exchange(r, HG_GHOST_ROWS));
-            if (has_pen) mg_down0_kernel<T, true><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, DOWN_H, true>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
+            if (stream_legs()) launch_sl_down(g, r, coarse[0], done);
+            else if (has_pen) mg_down0_kernel<T, true><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, DOWN_H, true>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
             else if (scalar_legs) mg_down0_kernel<T, false><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, DOWN_H, false>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
             else mg_down0v_kernel<T><<<tile_grid(), VR_THREADS, sizeof(VRegionSmem<T>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
             ++launches;
@@ -636,11 +654,34 @@ struct Solver : SolverBase {
         Coarse<T> c0;
         memset(&c0, 0, sizeof c0);
         if (nl > 0) c0 = coarse[0];
-        if (has_pen) mg_up0_kernel<T, true><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, UP_H, true>), stream>>>(g, d_code, r, z, c0, nl > 0, d_tile_active, part_rz, done);
+        if (stream_legs()) launch_sl_up(g, r, z, c0, nl > 0, done);
+        else if (has_pen) mg_up0_kernel<T, true><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, UP_H, true>), stream>>>(g, d_code, r, z, c0, nl > 0, d_tile_active, part_rz, done);
         else if (scalar_legs) mg_up0_kernel<T, false><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, UP_H, false>), stream>>>(g, d_code, r, z, c0, nl > 0, d_tile_active, part_rz, done);
         else mg_up0v_kernel<T><<<tile_grid(), VR_THREADS, sizeof(VRegionSmem<T>), stream>>>(g, d_code, r, z, c0, nl > 0, d_tile_active, part_rz, done);
         ++launches;
         return HG_OK;
+    }
+
+    // the streaming legs serve every configuration without gradient-penalty edges
+    bool stream_legs() const { return !has_pen && !tile_legs && !scalar_legs; }
+    bool has_soft() const { return d_soft != nullptr || soft_scalar != 0.0; }
+    dim3 sl_grid() const { return dim3((sl_ns + SL_SPB - 1) / SL_SPB, sl_nt, (K + 3) / 4); }
+    dim3 sl_block() const { return dim3(32, SL_SPB, std::min(K, 4)); }
+    void launch_sl_down(const Grid<T>& g, const T* r, const Coarse<T>& c1, const int* done) {
+        if (has_soft()) sl_down_kernel<T, true><<<sl_grid(), sl_block(), 0, stream>>>(g, d_code, r, c1, d_sl_down, sl_ns, done);
+        else sl_down_kernel<T, false><<<sl_grid(), sl_block(), 0, stream>>>(g, d_code, r, c1, d_sl_down, sl_ns, done);
+    }
+    void launch_sl_up(const Grid<T>& g, const T* r, T* z, const Coarse<T>& c1, int have_coarse, const int* done) {
+        if (has_soft()) sl_up_kernel<T, true><<<sl_grid(), sl_block(), 0, stream>>>(g, d_code, r, z, c1, have_coarse, d_sl_up, sl_ns, d_spart, done);
+        else sl_up_kernel<T, false><<<sl_grid(), sl_block(), 0, stream>>>(g, d_code, r, z, c1, have_coarse, d_sl_up, sl_ns, d_spart, done);
+    }
+    // scalar stage after the V-cycle: r.z from the partial sums the upward leg left (owned rows only)
+    int stage_beta_rz(int init) {
+        if (stream_legs()) {
+            const int t0 = ghost_top / SL_R, t1 = ghost_bottom ? (rows - ghost_bottom) / SL_R : sl_nt;
+            return stage_beta(d_spart + (long long)t0 * sl_ns, (t1 - t0) * sl_ns, (long long)sl_ns * sl_nt, init);
+        }
+        return stage_beta(tile_part(d_tpart1), n_own_tiles(), ntiles(), init);
     }
 
     int mg_levels() override { return 1 + (int)coarse.size(); }
@@ -1000,7 +1041,7 @@ struct Solver : SolverBase {
             if (kRefine) CU(cudaMemsetAsync(d_x, 0, vbytes, stream));
             if (mg) {
                 HGTRY(vcycle(d_z, d_r, done, d_tpart1));
-                HGTRY(stage_beta(tile_part(d_tpart1), n_own_tiles(), nt, 1));
+                HGTRY(stage_beta_rz(1));
                 cg_pupdate_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, d_p, d_z, d_tile_active, 1);
                 launches += 2;
             } else {
@@ -1020,7 +1061,7 @@ struct Solver : SolverBase {
                         cg_update_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, e, d_r, d_p, d_q, d_tile_active, d_tpart0);
                         HGTRY(stage_check(tile_part(d_tpart0), n_own_tiles(), nt));
                         HGTRY(vcycle(d_z, d_r, done, d_tpart1));
-                        HGTRY(stage_beta(tile_part(d_tpart1), n_own_tiles(), nt, 0));
+                        HGTRY(stage_beta_rz(0));
                         cg_pupdate_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, d_p, d_z, d_tile_active, 0);
                         launches += 6;
                     } else {
