@@ -37,7 +37,7 @@ namespace hg {
 
 #define SL_OUT 120        // columns a warp owns
 #define SL_R 64           // rows per chunk
-#define SL_SPB 2          // strips (warps) per block and channel
+#define SL_SPB 2          // tasks (warps) per block and channel
 
 // activity of the chunks: 0 = no free pixel within the chunk grown by `halo` (skipped), 1 = simple
 // (every pixel the warp reads is hard or a regular interior pixel -- code 0xAA, no soft weight: the
@@ -159,6 +159,7 @@ struct SlDown {
     const T* rk;                 // this channel's plane of r
     Coarse<T> cl;
     T* bk; T* xk;                // this channel's planes of the next level
+    int zero_x;                  // also clear x of the next level (only the unfused coarse path needs it)
     int i0, lane;
     bool owner;                  // lanes 1..30 own their columns
     T wjm[2], wjp[2];            // restriction weights of the lane's two coarse columns
@@ -192,8 +193,11 @@ struct SlDown {
                     T vb = s1.v[2] + wim * (wjm[1] * s2.v[1] + wjp[1] * s2.v[3]) + wip * (wjm[1] * s0.v[1] + wjp[1] * s0.v[3]);
                     if (Ja + 1 >= cl.cols) vb = T(0);
                     const long long oc = (long long)I * cl.pitch + Ja;
-                    sts2(bk + oc, va, vb);
-                    sts2(xk + oc, T(0), T(0));
+                    // inactive coarse pixels keep the zeros they were created with
+                    if (*reinterpret_cast<const unsigned short*>(cl.code + oc)) {
+                        sts2(bk + oc, va, vb);
+                        if (zero_x) sts2(xk + oc, T(0), T(0));
+                    }
                 }
             }
         }
@@ -228,41 +232,61 @@ struct SlDown {
 // All weights are 1/4 and the inverse diagonal is 1 at free pixels (code byte != 0), 0 elsewhere.  The
 // row window lives in rings of eight slots (row i <-> slot i & 7) and the loop is unrolled eight
 // steps, so every slot index is a compile-time constant and the rotation costs no register moves.
+// cp.async (LDGSTS) helpers: a lane's private FIFO in shared memory takes the place of prefetch registers
+__device__ __forceinline__ void sl_cp16(void* smem, const void* gmem, bool valid) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    const int bytes = valid ? 16 : 0;        // 0: nothing is read, the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sl_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void sl_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+#define SL_RING 8         // slots of the row rings (row i <-> slot i & 7)
+#define SL_PD 3           // r is requested this many rows ahead (codes two rows earlier still)
+
 template <typename T>
 struct SlLean {
     const uint8_t* code;
     const T* rk;
+    T* ring;              // this lane's quad in slot 0 of the warp's ring of r rows (shared memory); slots are 128 T apart
     int rows, pitch, c0, i0;
     bool colin, owner;
-    V4<T> Z[8], R[8];
+    V4<T> Z[8];
     unsigned M[8];
     __device__ __forceinline__ unsigned load_code(int i) const {
         return (colin && i >= 0 && i < rows) ? *reinterpret_cast<const unsigned*>(code + (long long)i * pitch + c0) : 0u;
     }
-    __device__ __forceinline__ V4<T> load_r(int i, unsigned m) const {
-        if (m) return ld4(rk + (long long)i * pitch + c0);
-        return zero4<T>();
+    // request row i of r into slot `slot` (zeros where the quad has no free pixel); one commit group per row
+    __device__ __forceinline__ void request(int i, int slot, unsigned m) {
+        const T* src = m ? rk + (long long)i * pitch + c0 : rk;
+        T* dst = ring + slot * 128;
+        sl_cp16(dst, src, m != 0u);
+        if (sizeof(T) == 8) sl_cp16(dst + 2, src + 2, m != 0u);
+        sl_cp_commit();
     }
+    __device__ __forceinline__ V4<T> row(int slot) const { return ld4(ring + slot * 128); }
     __device__ __forceinline__ void init(int ibeg, int slot0) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { Z[q] = zero4<T>(); R[q] = zero4<T>(); M[q] = 0u; }
-        // rows ibeg .. ibeg + 3 of the codes, ibeg .. ibeg + 2 of r  (slot0 = ibeg & 7, a compile-time fact of the caller)
-        M[slot0 & 7] = load_code(ibeg); M[(slot0 + 1) & 7] = load_code(ibeg + 1);
-        M[(slot0 + 2) & 7] = load_code(ibeg + 2); M[(slot0 + 3) & 7] = load_code(ibeg + 3);
-        R[slot0 & 7] = load_r(ibeg, M[slot0 & 7]);
-        R[(slot0 + 1) & 7] = load_r(ibeg + 1, M[(slot0 + 1) & 7]);
-        R[(slot0 + 2) & 7] = load_r(ibeg + 2, M[(slot0 + 2) & 7]);
+        for (int q = 0; q < 8; ++q) { Z[q] = zero4<T>(); M[q] = 0u; }
+        // codes of rows ibeg .. ibeg + SL_PD + 1, r of rows ibeg .. ibeg + SL_PD - 1  (slot0 = ibeg & 7, a compile-time fact of the caller)
+#pragma unroll
+        for (int q = 0; q < SL_PD + 2; ++q) M[(slot0 + q) & 7] = load_code(ibeg + q);
+#pragma unroll
+        for (int q = 0; q < SL_PD; ++q) request(ibeg + q, (slot0 + q) & 7, M[(slot0 + q) & 7]);
     }
-    template <int C> __device__ __forceinline__ void prefetch(int i) {
-        M[(C + 4) & 7] = load_code(i + 4);
-        R[(C + 3) & 7] = load_r(i + 3, M[(C + 3) & 7]);
+    // at the top of step i (slot C): code of row i + SL_PD + 2, request for row i + SL_PD; returns row i of r
+    template <int C> __device__ __forceinline__ V4<T> advance(int i) {
+        M[(C + SL_PD + 2) & 7] = load_code(i + SL_PD + 2);
+        request(i + SL_PD, (C + SL_PD) & 7, M[(C + SL_PD) & 7]);
+        sl_cp_wait<SL_PD>();
+        return row(C);
     }
-    // red pixels of row i (slot C): z = r where free
-    template <int C, int PAR> __device__ __forceinline__ void red_first(const T addA, const T addB) {
+    // red pixels of row i (slot C): z = r (+ add) where free
+    template <int C, int PAR> __device__ __forceinline__ void red_first(const V4<T>& rc, const T addA, const T addB) {
         const unsigned m = M[C];
         Z[C] = zero4<T>();
-        Z[C].v[PAR] = (m & (0xffu << (8 * PAR))) ? R[C].v[PAR] + addA : T(0);
-        Z[C].v[PAR + 2] = (m & (0xffu << (8 * (PAR + 2)))) ? R[C].v[PAR + 2] + addB : T(0);
+        Z[C].v[PAR] = (m & (0xffu << (8 * PAR))) ? rc.v[PAR] + addA : T(0);
+        Z[C].v[PAR + 2] = (m & (0xffu << (8 * (PAR + 2)))) ? rc.v[PAR + 2] + addB : T(0);
     }
     // 1/4 of the four neighbours of the pixels PAR, PAR + 2 of slot C (rows above / below: slots CU, CD)
     template <int C, int CU, int CD, int PAR> __device__ __forceinline__ void nsum(T& nA, T& nB) const {
@@ -272,13 +296,13 @@ struct SlLean {
         nA = T(0.25) * ((Z[CU].v[PAR] + Z[CD].v[PAR]) + (lfA + rtA));
         nB = T(0.25) * ((Z[CU].v[PAR + 2] + Z[CD].v[PAR + 2]) + (lfB + rtB));
     }
-    // Gauss-Seidel update of the pixels PAR, PAR + 2 of slot C
-    template <int C, int CU, int CD, int PAR> __device__ __forceinline__ void update() {
+    // Gauss-Seidel update of the pixels PAR, PAR + 2 of slot C with right-hand side rc
+    template <int C, int CU, int CD, int PAR> __device__ __forceinline__ void update(const V4<T>& rc) {
         T nA, nB;
         nsum<C, CU, CD, PAR>(nA, nB);
         const unsigned m = M[C];
-        Z[C].v[PAR] = (m & (0xffu << (8 * PAR))) ? R[C].v[PAR] + nA : T(0);
-        Z[C].v[PAR + 2] = (m & (0xffu << (8 * (PAR + 2)))) ? R[C].v[PAR + 2] + nB : T(0);
+        Z[C].v[PAR] = (m & (0xffu << (8 * PAR))) ? rc.v[PAR] + nA : T(0);
+        Z[C].v[PAR + 2] = (m & (0xffu << (8 * (PAR + 2)))) ? rc.v[PAR + 2] + nB : T(0);
     }
 };
 
@@ -286,6 +310,8 @@ template <typename T>
 struct SlLeanDown : SlLean<T> {
     using B = SlLean<T>;
     T* bk; T* xk;
+    const uint8_t* ccode;
+    int zero_x;
     int grows, crows, ccols, cpitch;
     T wjm[2], wjp[2];
     V4<T> S[8];
@@ -294,9 +320,9 @@ struct SlLeanDown : SlLean<T> {
         constexpr int C = (5 + U) & 7, C1 = (C + 7) & 7, C2 = (C + 6) & 7, C3 = (C + 5) & 7, C4 = (C + 4) & 7;
         constexpr int PAR = (5 + U) & 1;
         const int i = ib + U;
-        B::template prefetch<C>(i);
-        B::template red_first<C, PAR>(T(0), T(0));
-        B::template update<C1, C2, C, PAR>();                  // black pixels of row i - 1
+        const V4<T> rc = B::template advance<C>(i);
+        B::template red_first<C, PAR>(rc, T(0), T(0));
+        B::template update<C1, C2, C, PAR>(B::row(C1));        // black pixels of row i - 1
         {   // residual at the red pixels of row i - 2
             T nA, nB;
             B::template nsum<C2, C3, C1, PAR>(nA, nB);
@@ -316,8 +342,10 @@ struct SlLeanDown : SlLean<T> {
                     T vb = S[C3].v[2] + wim * (wjm[1] * S[C4].v[1] + wjp[1] * S[C4].v[3]) + wip * (wjm[1] * S[C2].v[1] + wjp[1] * S[C2].v[3]);
                     if (Ja + 1 >= ccols) vb = T(0);
                     const long long oc = (long long)I * cpitch + Ja;
-                    sts2(bk + oc, va, vb);
-                    sts2(xk + oc, T(0), T(0));
+                    if (*reinterpret_cast<const unsigned short*>(ccode + oc)) {
+                        sts2(bk + oc, va, vb);
+                        if (zero_x) sts2(xk + oc, T(0), T(0));
+                    }
                 }
             }
         }
@@ -330,6 +358,7 @@ struct SlLeanDown : SlLean<T> {
         for (int ib = B::i0 - 3; ib < B::i0 + SL_R + 3; ib += 8) {
             step<0>(ib); step<1>(ib); step<2>(ib); step<3>(ib); step<4>(ib); step<5>(ib); step<6>(ib); step<7>(ib);
         }
+        sl_cp_wait<0>();
     }
 };
 
@@ -358,20 +387,21 @@ struct SlLeanUp : SlLean<T> {
         constexpr int PAR = U & 1;
         constexpr int EA = (3 + U / 2) & 3, EB = (EA + 1) & 3, EN = (EA + 2) & 3;      // (ib >> 1) & 3 == 3
         const int i = ib + U;
-        B::template prefetch<C>(i);
+        const V4<T> rc = B::template advance<C>(i);
         if (PAR == 0) {
             load_e<EN>((i >> 1) + 2);
-            B::template red_first<C, 0>(E[EA][0], E[EA][1]);
+            B::template red_first<C, 0>(rc, E[EA][0], E[EA][1]);
         } else {
-            B::template red_first<C, 1>(T(0.25) * ((E[EA][0] + E[EA][1]) + (E[EB][0] + E[EB][1])),
+            B::template red_first<C, 1>(rc, T(0.25) * ((E[EA][0] + E[EA][1]) + (E[EB][0] + E[EB][1])),
                                         T(0.25) * ((E[EA][1] + E[EA][2]) + (E[EB][1] + E[EB][2])));
         }
-        B::template update<C1, C2, C, PAR>();                  // black pixels of row i - 1
-        B::template update<C2, C3, C1, PAR>();                 // red pixels of row i - 2 again
+        B::template update<C1, C2, C, PAR>(B::row(C1));        // black pixels of row i - 1
+        const V4<T> r2 = B::row(C2);
+        B::template update<C2, C3, C1, PAR>(r2);               // red pixels of row i - 2 again
         const int io = i - 2;
         if (io >= B::i0 && io < B::i0 + SL_R && B::owner && B::M[C2]) {
 #pragma unroll
-            for (int p = 0; p < 4; ++p) acc += (double)(B::Z[C2].v[p] * B::R[C2].v[p]);
+            for (int p = 0; p < 4; ++p) acc += (double)(B::Z[C2].v[p] * r2.v[p]);
             st4(zk + (long long)io * B::pitch + B::c0, B::Z[C2]);
         }
     }
@@ -384,53 +414,56 @@ struct SlLeanUp : SlLean<T> {
         for (int ib = B::i0 - 2; ib < B::i0 + SL_R + 2; ib += 8) {
             step<0>(ib); step<1>(ib); step<2>(ib); step<3>(ib); step<4>(ib); step<5>(ib); step<6>(ib); step<7>(ib);
         }
+        sl_cp_wait<0>();
     }
 };
 
-template <typename T, bool SOFT>
-__global__ void __launch_bounds__(32 * SL_SPB * 4)
-sl_down_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict__ r, Coarse<T> cl, const uint8_t* __restrict__ active,
-               int ns, const int* __restrict__ done) {
+// this lane's slot-0 quad in the warp's shared-memory ring (dynamic shared memory: SL_RING x 128 T per warp)
+template <typename T> __device__ __forceinline__ T* sl_ring() {
+    extern __shared__ __align__(16) unsigned char sl_smem[];
+    const int warp = threadIdx.z * blockDim.y + threadIdx.y;
+    return reinterpret_cast<T*>(sl_smem) + (warp * SL_RING * 32 + threadIdx.x) * 4;
+}
+
+// One warp per task (chunk) and channel; `tasks` lists the chunks of one kind (lean or general).
+template <typename T, bool SOFT, bool LEAN>
+__global__ void __launch_bounds__(32 * SL_SPB * 4, LEAN ? (sizeof(T) == 4 ? 4 : 2) : 1)
+sl_down_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict__ r, Coarse<T> cl, const int* __restrict__ tasks,
+               int ntasks, int ns, int zero_x, const int* __restrict__ done) {
     if (done && *done) return;
-    const int s = blockIdx.x * SL_SPB + threadIdx.y, t = blockIdx.y, k = blockIdx.z * blockDim.z + threadIdx.z;
-    if (s >= ns || k >= g.K) return;
-    const unsigned act = active[t * ns + s];
-    if (!act) return;
-    if (act == 1u) {
-        SlLeanDown<T> f;
-        f.code = code; f.rk = r + k * g.plane;
-        f.rows = g.rows; f.pitch = g.pitch; f.i0 = t * SL_R;
-        f.c0 = s * SL_OUT - 4 + 4 * (int)threadIdx.x;
-        f.colin = f.c0 >= 0 && f.c0 < g.pitch;
-        f.owner = threadIdx.x >= 1 && threadIdx.x <= 30;
-        f.bk = cl.b + k * cl.plane; f.xk = cl.x + k * cl.plane;
-        f.grows = g.rows; f.crows = cl.rows; f.ccols = cl.cols; f.cpitch = cl.pitch;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int J = (f.c0 >> 1) + q;
-            f.wjm[q] = (T)w1d(-1, J, g.cols, cl.cols);
-            f.wjp[q] = (T)w1d(1, J, g.cols, cl.cols);
-        }
-        f.run();
-        return;
-    }
-    SlDown<T, SOFT> d;
-    d.lane = threadIdx.x;
-    d.cx.g = g; d.cx.code = code;
-    d.cx.c0 = s * SL_OUT - 4 + 4 * d.lane;
-    d.cx.colin = d.cx.c0 >= 0 && d.cx.c0 < g.pitch;
-    d.owner = d.lane >= 1 && d.lane <= 30;
-    d.rk = r + k * g.plane;
-    d.cl = cl;
-    d.bk = cl.b + k * cl.plane; d.xk = cl.x + k * cl.plane;
-    d.i0 = t * SL_R;
+    const int idx = blockIdx.x * SL_SPB + threadIdx.y, k = blockIdx.y * blockDim.z + threadIdx.z;
+    if (idx >= ntasks || k >= g.K) return;
+    const int task = tasks[idx], t = task / ns, s = task - t * ns;
+    const int c0 = s * SL_OUT - 4 + 4 * (int)threadIdx.x;
+    const bool colin = c0 >= 0 && c0 < g.pitch, owner = threadIdx.x >= 1 && threadIdx.x <= 30;
+    T wjm[2], wjp[2];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-        const int J = (d.cx.c0 >> 1) + q;
-        d.wjm[q] = (T)w1d(-1, J, g.cols, cl.cols);
-        d.wjp[q] = (T)w1d(1, J, g.cols, cl.cols);
+        const int J = (c0 >> 1) + q;
+        wjm[q] = (T)w1d(-1, J, g.cols, cl.cols);
+        wjp[q] = (T)w1d(1, J, g.cols, cl.cols);
     }
-    d.run();
+    if (LEAN) {
+        SlLeanDown<T> f;
+        f.ring = sl_ring<T>();
+        f.code = code; f.rk = r + k * g.plane;
+        f.rows = g.rows; f.pitch = g.pitch; f.i0 = t * SL_R;
+        f.c0 = c0; f.colin = colin; f.owner = owner;
+        f.bk = cl.b + k * cl.plane; f.xk = cl.x + k * cl.plane; f.ccode = cl.code; f.zero_x = zero_x;
+        f.grows = g.rows; f.crows = cl.rows; f.ccols = cl.cols; f.cpitch = cl.pitch;
+        f.wjm[0] = wjm[0]; f.wjm[1] = wjm[1]; f.wjp[0] = wjp[0]; f.wjp[1] = wjp[1];
+        f.run();
+    } else {
+        SlDown<T, SOFT> d;
+        d.lane = threadIdx.x;
+        d.cx.g = g; d.cx.code = code; d.cx.c0 = c0; d.cx.colin = colin; d.owner = owner;
+        d.rk = r + k * g.plane;
+        d.cl = cl; d.zero_x = zero_x;
+        d.bk = cl.b + k * cl.plane; d.xk = cl.x + k * cl.plane;
+        d.i0 = t * SL_R;
+        d.wjm[0] = wjm[0]; d.wjm[1] = wjm[1]; d.wjp[0] = wjp[0]; d.wjp[1] = wjp[1];
+        d.run();
+    }
 }
 
 // ---- upward leg -----------------------------------------------------------------------------------------
@@ -526,42 +559,40 @@ struct SlUp {
     }
 };
 
-template <typename T, bool SOFT>
-__global__ void __launch_bounds__(32 * SL_SPB * 4)
+template <typename T, bool SOFT, bool LEAN>
+__global__ void __launch_bounds__(32 * SL_SPB * 4, LEAN ? (sizeof(T) == 4 ? 3 : 1) : 1)
 sl_up_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict__ r, T* __restrict__ z, Coarse<T> cl, int have_coarse,
-             const uint8_t* __restrict__ active, int ns, double* __restrict__ part_rz, const int* __restrict__ done) {
+             const int* __restrict__ tasks, int ntasks, int ns, int nt, double* __restrict__ part_rz, const int* __restrict__ done) {
     if (done && *done) return;
-    const int s = blockIdx.x * SL_SPB + threadIdx.y, t = blockIdx.y, k = blockIdx.z * blockDim.z + threadIdx.z;
-    if (s >= ns || k >= g.K) return;
-    const unsigned act = active[t * ns + s];
-    if (!act) return;
-    if (act == 1u) {
+    const int idx = blockIdx.x * SL_SPB + threadIdx.y, k = blockIdx.y * blockDim.z + threadIdx.z;
+    if (idx >= ntasks || k >= g.K) return;
+    const int task = tasks[idx], t = task / ns, s = task - t * ns;
+    const int c0 = s * SL_OUT - 4 + 4 * (int)threadIdx.x;
+    const bool colin = c0 >= 0 && c0 < g.pitch, owner = threadIdx.x >= 1 && threadIdx.x <= 30;
+    double acc;
+    if (LEAN) {
         SlLeanUp<T> f;
+        f.ring = sl_ring<T>();
         f.code = code; f.rk = r + k * g.plane; f.zk = z + k * g.plane;
         f.rows = g.rows; f.pitch = g.pitch; f.i0 = t * SL_R;
-        f.c0 = s * SL_OUT - 4 + 4 * (int)threadIdx.x;
-        f.colin = f.c0 >= 0 && f.c0 < g.pitch;
-        f.owner = threadIdx.x >= 1 && threadIdx.x <= 30;
+        f.c0 = c0; f.colin = colin; f.owner = owner;
         f.ek = have_coarse ? cl.x + k * cl.plane : nullptr;
         f.crows = cl.rows; f.ccols = cl.cols; f.cpitch = cl.pitch;
         f.run();
-        const double sdot = warp_sum(f.acc);
-        if (threadIdx.x == 0) part_rz[(long long)k * (ns * gridDim.y) + (long long)t * ns + s] = sdot;
-        return;
+        acc = f.acc;
+    } else {
+        SlUp<T, SOFT> u;
+        u.lane = threadIdx.x;
+        u.cx.g = g; u.cx.code = code; u.cx.c0 = c0; u.cx.colin = colin; u.owner = owner;
+        u.rk = r + k * g.plane; u.zk = z + k * g.plane;
+        u.ek = have_coarse ? cl.x + k * cl.plane : nullptr;
+        u.crows = cl.rows; u.ccols = cl.cols; u.cpitch = cl.pitch;
+        u.i0 = t * SL_R;
+        u.run();
+        acc = u.acc;
     }
-    SlUp<T, SOFT> u;
-    u.lane = threadIdx.x;
-    u.cx.g = g; u.cx.code = code;
-    u.cx.c0 = s * SL_OUT - 4 + 4 * u.lane;
-    u.cx.colin = u.cx.c0 >= 0 && u.cx.c0 < g.pitch;
-    u.owner = u.lane >= 1 && u.lane <= 30;
-    u.rk = r + k * g.plane; u.zk = z + k * g.plane;
-    u.ek = have_coarse ? cl.x + k * cl.plane : nullptr;
-    u.crows = cl.rows; u.ccols = cl.cols; u.cpitch = cl.pitch;
-    u.i0 = t * SL_R;
-    u.run();
-    const double sdot = warp_sum(u.acc);
-    if (u.lane == 0) part_rz[(long long)k * (ns * gridDim.y) + (long long)t * ns + s] = sdot;
+    const double sdot = warp_sum(acc);
+    if (threadIdx.x == 0) part_rz[(long long)k * ((long long)ns * nt) + task] = sdot;
 }
 
 }  // namespace hg

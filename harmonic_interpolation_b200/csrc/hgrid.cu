@@ -177,6 +177,8 @@ struct Solver : SolverBase {
     uint8_t *d_sl_up = nullptr, *d_sl_down = nullptr;
     double* d_spart = nullptr;
     int sl_ns = 0, sl_nt = 0;
+    int* d_sl_tasks = nullptr;
+    int sl_off[4] = {0, 0, 0, 0}, sl_n_down_lean = 0, sl_n_down_gen = 0, sl_n_up_lean = 0, sl_n_up_gen = 0;
     bool tile_legs = getenv("HGRID_TILE_LEGS") != nullptr;       // debugging aid: the shared-memory legs of fine_vec.cuh
     bool scalar_legs = getenv("HGRID_SCALAR_LEGS") != nullptr;
     bool unfused_coarse = getenv("HGRID_UNFUSED_COARSE") != nullptr;   // debugging aid: one kernel per colour / transfer (mg.cuh)   // debugging aid: the scalar fused legs of fine.cuh
@@ -198,7 +200,7 @@ struct Solver : SolverBase {
         if (kRefine) { cudaFree(d_xm); cudaFree(d_bm); }
         cudaFree(d_tile_active); cudaFree(d_tpart0); cudaFree(d_tpart1);
         cudaFree(d_down_active); cudaFree(d_code); cudaFree(d_lpart);
-        cudaFree(d_sl_up); cudaFree(d_sl_down); cudaFree(d_spart);
+        cudaFree(d_sl_up); cudaFree(d_sl_down); cudaFree(d_spart); cudaFree(d_sl_tasks);
         if (comm && g_nccl.ok) g_nccl.CommDestroy(comm);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -533,10 +535,35 @@ struct Solver : SolverBase {
         CU(cudaMemsetAsync(d_spart, 0, (size_t)sl_ns * sl_nt * K * sizeof(double), stream));
         sl_activity_kernel<<<dim3(sl_ns, sl_nt), 256, 0, stream>>>(d_flags, d_code, rows, cols, pitch, 0, sl_ns, d_sl_up);
         sl_activity_kernel<<<dim3(sl_ns, sl_nt), 256, 0, stream>>>(d_flags, d_code, rows, cols, pitch, 1, sl_ns, d_sl_down);
+        {   // task lists: [down lean | down general | up lean | up general], in row-major chunk order
+            const int n = sl_ns * sl_nt;
+            std::vector<uint8_t> hu(n), hd(n);
+            CU(cudaMemcpyAsync(hu.data(), d_sl_up, n, cudaMemcpyDeviceToHost, stream));
+            CU(cudaMemcpyAsync(hd.data(), d_sl_down, n, cudaMemcpyDeviceToHost, stream));
+            CU(cudaStreamSynchronize(stream));
+            std::vector<int> lists;
+            lists.reserve(2 * n);
+            int* cnt[4] = {&sl_n_down_lean, &sl_n_down_gen, &sl_n_up_lean, &sl_n_up_gen};
+            for (int which = 0; which < 4; ++which) {
+                const std::vector<uint8_t>& a = which < 2 ? hd : hu;
+                const uint8_t want = (which & 1) ? 2 : 1;
+                sl_off[which] = (int)lists.size();
+                for (int e = 0; e < n; ++e)
+                    if (a[e] == want) lists.push_back(e);
+                *cnt[which] = (int)lists.size() - sl_off[which];
+            }
+            cudaFree(d_sl_tasks);
+            d_sl_tasks = nullptr;
+            CU(cudaMalloc(&d_sl_tasks, std::max<size_t>(1, lists.size()) * sizeof(int)));
+            if (!lists.empty()) CU(cudaMemcpyAsync(d_sl_tasks, lists.data(), lists.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+            CU(cudaStreamSynchronize(stream));
+        }
         CU(cudaFuncSetAttribute(mg_down0_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, DOWN_H, false>)));
         CU(cudaFuncSetAttribute(mg_down0_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, DOWN_H, true>)));
         CU(cudaFuncSetAttribute(mg_up0_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, UP_H, false>)));
         CU(cudaFuncSetAttribute(mg_up0_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, UP_H, true>)));
+        CU(cudaFuncSetAttribute(sl_down_kernel<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_SPB * 4 * SL_RING * 128 * sizeof(T))));
+        CU(cudaFuncSetAttribute(sl_up_kernel<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_SPB * 4 * SL_RING * 128 * sizeof(T))));
         CU(cudaFuncSetAttribute(mg_down0v_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VRegionSmem<T>)));
         CU(cudaFuncSetAttribute(mg_up0v_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VRegionSmem<T>)));
         return HG_OK;
@@ -665,15 +692,27 @@ struct Solver : SolverBase {
     // the streaming legs serve every configuration without gradient-penalty edges
     bool stream_legs() const { return !has_pen && !tile_legs && !scalar_legs; }
     bool has_soft() const { return d_soft != nullptr || soft_scalar != 0.0; }
-    dim3 sl_grid() const { return dim3((sl_ns + SL_SPB - 1) / SL_SPB, sl_nt, (K + 3) / 4); }
+    dim3 sl_grid(int ntasks) const { return dim3((ntasks + SL_SPB - 1) / SL_SPB, (K + 3) / 4); }
     dim3 sl_block() const { return dim3(32, SL_SPB, std::min(K, 4)); }
+    size_t sl_smem() const { return (size_t)SL_SPB * std::min(K, 4) * SL_RING * 128 * sizeof(T); }   // lean kernels: one ring of r rows per warp
     void launch_sl_down(const Grid<T>& g, const T* r, const Coarse<T>& c1, const int* done) {
-        if (has_soft()) sl_down_kernel<T, true><<<sl_grid(), sl_block(), 0, stream>>>(g, d_code, r, c1, d_sl_down, sl_ns, done);
-        else sl_down_kernel<T, false><<<sl_grid(), sl_block(), 0, stream>>>(g, d_code, r, c1, d_sl_down, sl_ns, done);
+        const int zx = unfused_coarse ? 1 : 0;
+        if (sl_n_down_lean)
+            sl_down_kernel<T, false, true><<<sl_grid(sl_n_down_lean), sl_block(), sl_smem(), stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[0], sl_n_down_lean, sl_ns, zx, done);
+        if (sl_n_down_gen) {
+            if (has_soft()) sl_down_kernel<T, true, false><<<sl_grid(sl_n_down_gen), sl_block(), 0, stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[1], sl_n_down_gen, sl_ns, zx, done);
+            else sl_down_kernel<T, false, false><<<sl_grid(sl_n_down_gen), sl_block(), 0, stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[1], sl_n_down_gen, sl_ns, zx, done);
+        }
+        launches += (sl_n_down_lean > 0) + (sl_n_down_gen > 0) - 1;
     }
     void launch_sl_up(const Grid<T>& g, const T* r, T* z, const Coarse<T>& c1, int have_coarse, const int* done) {
-        if (has_soft()) sl_up_kernel<T, true><<<sl_grid(), sl_block(), 0, stream>>>(g, d_code, r, z, c1, have_coarse, d_sl_up, sl_ns, d_spart, done);
-        else sl_up_kernel<T, false><<<sl_grid(), sl_block(), 0, stream>>>(g, d_code, r, z, c1, have_coarse, d_sl_up, sl_ns, d_spart, done);
+        if (sl_n_up_lean)
+            sl_up_kernel<T, false, true><<<sl_grid(sl_n_up_lean), sl_block(), sl_smem(), stream>>>(g, d_code, r, z, c1, have_coarse, d_sl_tasks + sl_off[2], sl_n_up_lean, sl_ns, sl_nt, d_spart, done);
+        if (sl_n_up_gen) {
+            if (has_soft()) sl_up_kernel<T, true, false><<<sl_grid(sl_n_up_gen), sl_block(), 0, stream>>>(g, d_code, r, z, c1, have_coarse, d_sl_tasks + sl_off[3], sl_n_up_gen, sl_ns, sl_nt, d_spart, done);
+            else sl_up_kernel<T, false, false><<<sl_grid(sl_n_up_gen), sl_block(), 0, stream>>>(g, d_code, r, z, c1, have_coarse, d_sl_tasks + sl_off[3], sl_n_up_gen, sl_ns, sl_nt, d_spart, done);
+        }
+        launches += (sl_n_up_lean > 0) + (sl_n_up_gen > 0) - 1;
     }
     // scalar stage after the V-cycle: r.z from the partial sums the upward leg left (owned rows only)
     int stage_beta_rz(int init) {
