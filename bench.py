@@ -245,6 +245,14 @@ def main():
     alg_bytes_full = float(s.local_rows) * n * (K * 2 * W + 1)
     peak, peak_src = peaks()
     achieved = alg_bytes / (ms_apply * 1e-3) / 1e9
+    # DRAM traffic of that kernel per launch from the committed `ncu --set full` capture of this workload
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    kname = "lap_tile_kernel<%s, %s, 0, 1, 3, 0>" % (("float", "float") if W == 4 else ("double", "double"))
+    if os.path.isfile(tp) and n == 16384 and world == 1:
+        ent = json.load(open(tp)).get(kname)
+        if ent:
+            traffic, traffic_src = ent["dram_read_bytes"] + ent["dram_write_bytes"], ent["source"]
 
     if world > 1:
         dist.barrier()
@@ -266,8 +274,9 @@ def main():
                 "seconds_per_step": float(t_e2e.item()),
                 "api": "hg_solve_u8 via SlabSolver.solve_u8: uint8 RGB in pinned host memory -> uint8 RGB (pattern uploaded once, as with the reference's factor-once closure)"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "lap_apply_kernel<%s>" % ("float" if W == 4 else "double"),
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": kname + "  (q = A p and the partial sums of p.q: the stencil launch of every CG iteration)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_apply, "peak_source": peak_src,
                      "frac_of_8TBs_nominal": achieved / 8000.0,
                      "bytes_basis": "pixels of the tiles the kernel touches (tiles without a free pixel are skipped)",

@@ -5,7 +5,7 @@
 // working tile by tile in shared memory, so a level's planes cross HBM once per leg instead of
 // once per colour:
 //
-//   cdown_kernel   b_l  ->  x_l = S_pre(0, b_l),   b_{l+1} = R (b_l - A_l x_l),   x_{l+1} = 0
+//   cdown_kernel   b_l  ->  x_l = S_pre(0, b_l),   b_{l+1} = R (b_l - A_l x_l)
 //   cup_kernel     x_l  <-  S_post(x_l + P x_{l+1}, b_l)
 //
 // Colours: c = 2 (i & 1) + (j & 1), swept 0,1,2,3 on the way down and 3,2,1,0 on the way up.
@@ -223,6 +223,8 @@ __device__ __forceinline__ void cf_store_tile(const Coarse<T>& L, const CFSmem<T
         if (i >= L.rows || j >= L.pitch) continue;
         const int li = ii + CF_HT;
         const int ca = (li & 1) * 2, a = (li >> 1) + 1, t = 2 * u + (CF_HL >> 1) + 2;
+        // a quad without an active pixel is zero in memory already and is never written
+        if (!(S.C[ca][a][t] | S.C[ca + 1][a][t] | S.C[ca][a][t + 1] | S.C[ca + 1][a][t + 1])) continue;
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
             if (k >= kn) break;
@@ -247,17 +249,22 @@ cdown_kernel(Coarse<T> L, Coarse<T> Lc, const int* __restrict__ done) {
     const int k0 = blockIdx.z * KC, kn = min(KC, L.K - k0);
 
     cf_zero_guards(S);
-    cf_load_codes(L, gi0, gj0, S);
-    // right-hand side -> the pixels' own slots
+    // codes, and the right-hand side -> the pixels' own slots (quads without an active pixel are not read: b is 0 there)
     for (int e = threadIdx.x; e < CF_RH * (CF_RW / 4); e += CF_THREADS) {
         const int li = e / (CF_RW / 4), u = e - li * (CF_RW / 4);
         const int i = gi0 + li, j = gj0 + 4 * u;
         const bool in = i >= 0 && i < L.rows && j >= 0 && j < L.pitch;
         const int ca = (li & 1) * 2, a = (li >> 1) + 1, t = 2 * u + 2;
+        unsigned c4 = 0;
+        if (in) c4 = *reinterpret_cast<const unsigned*>(L.code + (long long)i * L.pitch + j);
+        S.C[ca][a][t] = (uint8_t)(c4 & 0xffu);
+        S.C[ca + 1][a][t] = (uint8_t)((c4 >> 8) & 0xffu);
+        S.C[ca][a][t + 1] = (uint8_t)((c4 >> 16) & 0xffu);
+        S.C[ca + 1][a][t + 1] = (uint8_t)(c4 >> 24);
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
             V4<T> v = zero4<T>();
-            if (in && k < kn) v = ld4(L.b + (k0 + k) * L.plane + (long long)i * L.pitch + j);
+            if (c4 != 0u && k < kn) v = ld4(L.b + (k0 + k) * L.plane + (long long)i * L.pitch + j);
             cf_sts2(&S.X[k][ca][a][t], v.v[0], v.v[2]);
             cf_sts2(&S.X[k][ca + 1][a][t], v.v[1], v.v[3]);
         }
@@ -290,12 +297,11 @@ cdown_kernel(Coarse<T> L, Coarse<T> Lc, const int* __restrict__ done) {
         const T wim = (T)w1d(-1, I, L.rows, Lc.rows), wip = (T)w1d(1, I, L.rows, Lc.rows);
         const T wjm = (T)w1d(-1, J, L.cols, Lc.cols), wjp = (T)w1d(1, J, L.cols, Lc.cols);
         const long long oc = (long long)I * Lc.pitch + J;
+        if (!Lc.code[oc]) continue;       // inactive next-coarser pixels keep the zeros they were created with
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
             if (k >= kn) break;
-            const T v = J < Lc.cols ? r0[k] + (wjm * rl[k] + wjp * rr[k]) + (wim * ru[k] + wip * rd[k]) : T(0);
-            Lc.b[(k0 + k) * Lc.plane + oc] = v;
-            Lc.x[(k0 + k) * Lc.plane + oc] = T(0);
+            Lc.b[(k0 + k) * Lc.plane + oc] = r0[k] + (wjm * rl[k] + wjp * rr[k]) + (wim * ru[k] + wip * rd[k]);
         }
     }
 }
@@ -337,7 +343,7 @@ cup_kernel(Coarse<T> L, Coarse<T> Lc, const int* __restrict__ done) {
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
             V4<T> v = zero4<T>();
-            if (in && k < kn) {
+            if (c4 != 0u && k < kn) {      // quads without an active pixel hold zeros and stay so
                 v = ld4(L.x + (k0 + k) * L.plane + (long long)i * L.pitch + j);
                 // pixels lj = 4u + p: next-coarser column 2u + (p >> 1) (+1 for odd lj)
                 const T e00 = S.SE[k][r][2 * u], e01 = S.SE[k][r][2 * u + 1], e02 = S.SE[k][r][2 * u + 2];
