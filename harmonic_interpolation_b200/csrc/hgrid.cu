@@ -17,6 +17,7 @@
 #include "fine_stream.cuh"
 #include "fine_vec.cuh"
 #include "mg.cuh"
+#include "mg25.cuh"
 #include "pcg.cuh"
 #include "stencil.cuh"
 
@@ -166,6 +167,10 @@ struct Solver : SolverBase {
     T* d_z = nullptr;
     std::vector<Coarse<T>> coarse;
     double* d_dense = nullptr;   // [A | A^-1] of the coarsest level
+    // bilaplacian: hierarchy of explicit 25-point stencils, level 0 included (mg25.cuh)
+    std::vector<Lev25<T>> lev25;
+    double* d_dense25 = nullptr;
+    int mg25_sweeps = getenv("HGRID_MG25_SWEEPS") ? atoi(getenv("HGRID_MG25_SWEEPS")) : 1;
     // tile path (Laplacian + multigrid): activity map and per-tile partial sums
     uint8_t* d_tile_active = nullptr;
     double *d_tpart0 = nullptr, *d_tpart1 = nullptr;
@@ -333,6 +338,13 @@ struct Solver : SolverBase {
         }
         cudaFree(d_dense); cudaFree(d_gdense);
         d_dense = d_gdense = nullptr;
+        for (size_t l = 0; l < lev25.size(); ++l) {
+            cudaFree(lev25[l].coef);
+            if (l > 0) { cudaFree(lev25[l].x); cudaFree(lev25[l].b); }
+        }
+        lev25.clear();
+        cudaFree(d_dense25);
+        d_dense25 = nullptr;
     }
 
     static int chain(int n, int levels) { for (int l = 0; l < levels; ++l) n = (n + 1) / 2; return n; }
@@ -500,6 +512,71 @@ struct Solver : SolverBase {
     }
 
     bool use_mg() const { return precond == HG_PRECOND_MULTIGRID && op == HG_OP_LAPLACIAN; }
+    bool use_mg25() const { return precond == HG_PRECOND_MULTIGRID && op == HG_OP_BILAPLACIAN; }
+
+    // ---- bilaplacian hierarchy --------------------------------------------------------------------
+    int build_hierarchy25() {
+        free_hierarchy();
+        if (!d_z) {
+            CU(cudaMalloc(&d_z, (size_t)plane * K * sizeof(T)));
+            CU(cudaMemsetAsync(d_z, 0, (size_t)plane * K * sizeof(T), stream));
+        }
+        int r = rows, c = cols;
+        for (int level = 0;; ++level) {
+            Lev25<T> L;
+            L.rows = r; L.cols = c;
+            L.pitch = level == 0 ? pitch : round_up(c, 32);
+            L.plane = (long long)L.rows * L.pitch;
+            L.K = K;
+            L.coef = L.x = L.b = nullptr;
+            CU(cudaMalloc(&L.coef, (size_t)L.plane * 25 * sizeof(T)));
+            if (level > 0) {
+                CU(cudaMalloc(&L.x, (size_t)L.plane * K * sizeof(T)));
+                CU(cudaMalloc(&L.b, (size_t)L.plane * K * sizeof(T)));
+                CU(cudaMemsetAsync(L.x, 0, (size_t)L.plane * K * sizeof(T), stream));
+                CU(cudaMemsetAsync(L.b, 0, (size_t)L.plane * K * sizeof(T), stream));
+            }
+            dim3 cg((L.pitch + 127) / 128, L.rows);
+            if (level == 0) assemble25_kernel<T><<<cg, 128, 0, stream>>>(grid(), L);
+            else galerkin25_kernel<T><<<cg, 128, 0, stream>>>(Acc25<T>{lev25.back()}, L);
+            lev25.push_back(L);
+            if ((long long)r * c <= 256) break;
+            r = (r + 1) / 2; c = (c + 1) / 2;
+        }
+        const Lev25<T>& L = lev25.back();
+        const int n = L.rows * L.cols;
+        CU(cudaMalloc(&d_dense25, (size_t)n * 2 * n * sizeof(double)));
+        CU(cudaMemsetAsync(d_dense25, 0, (size_t)n * 2 * n * sizeof(double), stream));
+        dense_fill25_kernel<T><<<(n + 127) / 128, 128, 0, stream>>>(L, d_dense25);
+        gauss_jordan_kernel<<<1, 1024, 2 * n * sizeof(double), stream>>>(d_dense25, n);
+        CU(cudaGetLastError());
+        return HG_OK;
+    }
+    void gs25(const Lev25<T>& L, bool forward, const int* done) {
+        dim3 gg(((L.cols + 2) / 3 + 127) / 128, (L.rows + 2) / 3);
+        for (int s = 0; s < mg25_sweeps; ++s)
+            for (int c = 0; c < 9; ++c) gs25_kernel<T><<<gg, 128, 0, stream>>>(L, forward ? c : 8 - c, done);
+        launches += 9 * mg25_sweeps;
+    }
+    // z = M^-1 r: one symmetric V-cycle from the zero guess on the 25-point hierarchy (level 0 works in place on z, r)
+    int vcycle25(T* z, T* r, const int* done) {
+        lev25[0].x = z; lev25[0].b = r;
+        CU(cudaMemsetAsync(z, 0, (size_t)plane * K * sizeof(T), stream));
+        const int n = (int)lev25.size();
+        for (int l = 0; l + 1 < n; ++l) {
+            gs25(lev25[l], true, done);
+            const Lev25<T>& Lc = lev25[l + 1];
+            resid_restrict25_kernel<T><<<dim3((Lc.pitch + 127) / 128, Lc.rows), 128, 0, stream>>>(lev25[l], Lc, done);
+        }
+        const Lev25<T>& Lb = lev25[n - 1];
+        coarsest_dense25_kernel<T><<<K, 256, Lb.rows * Lb.cols * sizeof(double), stream>>>(Lb, d_dense25, done);
+        for (int l = n - 2; l >= 0; --l) {
+            prolong_add25_kernel<T><<<dim3((lev25[l].cols + 255) / 256, lev25[l].rows), 256, 0, stream>>>(lev25[l], lev25[l + 1], done);
+            gs25(lev25[l], false, done);
+        }
+        launches += 2 * (n - 1) + 2;
+        return HG_OK;
+    }
 
     dim3 tile_grid() const { return dim3(tiles_x, tiles_y); }
 
@@ -754,6 +831,9 @@ struct Solver : SolverBase {
         if (use_mg()) {
             HGTRY(vcycle(d_z, d_r, nullptr, d_tpart1));
             export_kernel<T, T><<<pg, 256, 0, stream>>>(grid(), d_z, d_out);
+        } else if (use_mg25()) {
+            HGTRY(vcycle25(d_z, d_r, nullptr));
+            export_kernel<T, T><<<pg, 256, 0, stream>>>(grid(), d_z, d_out);
         } else {
             jacobi_apply_kernel<T><<<vec_blocks(), VEC_THREADS, 0, stream>>>(plane, K, d_q, d_r, d_dinv);
             export_kernel<T, T><<<pg, 256, 0, stream>>>(grid(), d_q, d_out);
@@ -775,6 +855,7 @@ struct Solver : SolverBase {
         diag_kernel<T><<<pg, 256, 0, stream>>>(grid(), op == HG_OP_BILAPLACIAN, d_dinv);
         has_pen = w_g != 0.0;   // refined below once the flag counts are known
         if (use_mg()) HGTRY(build_hierarchy());
+        else if (use_mg25()) HGTRY(build_hierarchy25());
         else free_hierarchy();
         unsigned long long counts[8];
         CU(cudaMemcpyAsync(counts, d_counts, sizeof counts, cudaMemcpyDeviceToHost, stream));
@@ -784,7 +865,7 @@ struct Solver : SolverBase {
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, ev0, ev1));
         if (info) {
-            info->levels = 1 + (int)coarse.size();
+            info->levels = use_mg25() ? (int)lev25.size() : 1 + (int)coarse.size();
             info->empty_rows = (int)counts[0];
             info->unreferenced = (int)counts[1];
             info->n_hard = (long long)counts[2];
@@ -1020,7 +1101,7 @@ struct Solver : SolverBase {
         if (!is_setup || !have_values) return fail(HG_ERR_INVALID, "hg_solve_device: values have not been uploaded");
         if (maxiter <= 0) maxiter = 100000;
         launches = 0;
-        const bool mg = use_mg();
+        const bool mg = use_mg(), mg25 = use_mg25();
         if (world > 1 && !mg) return fail(HG_ERR_INVALID, "the slab mode needs the multigrid preconditioner");
         const int nb_op = op_blocks(), nb_vec = vec_blocks();
         const dim3 pg((pitch + 255) / 256, rows);
@@ -1045,7 +1126,7 @@ struct Solver : SolverBase {
         // large grids: look at the state after every iteration (a sync costs microseconds, an
         // iteration milliseconds); small grids: enqueue batches, the surplus launches are no-ops
         const long long npix = (long long)rows * cols;
-        const int batch = npix >= (1LL << 22) ? 1 : (mg ? 4 : 32);
+        const int batch = npix >= (1LL << 22) ? 1 : ((mg || mg25) ? 4 : 32);
         const int nt = mg ? ntiles() : 0;
 
         CgState host;
@@ -1084,7 +1165,8 @@ struct Solver : SolverBase {
                 cg_pupdate_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, d_p, d_z, d_tile_active, 1);
                 launches += 2;
             } else {
-                jacobi_apply_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(plane, K, d_z, d_r, d_dinv);
+                if (mg25) HGTRY(vcycle25(d_z, d_r, done));
+                else jacobi_apply_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(plane, K, d_z, d_r, d_dinv);
                 cg_dot_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_r, d_z, d_part1);
                 HGTRY(stage_beta(d_part1, nb_vec, nb_vec, 1));
                 CU(cudaMemcpyAsync(d_p, d_z, vbytes, cudaMemcpyDeviceToDevice, stream));
@@ -1108,7 +1190,8 @@ struct Solver : SolverBase {
                         HGTRY(stage_alpha(d_part0, nb_op, nb_op));
                         cg_update_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, e, d_r, d_p, d_q, d_part0);
                         HGTRY(stage_check(d_part0, nb_vec, nb_vec));
-                        jacobi_apply_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(plane, K, d_z, d_r, d_dinv);
+                        if (mg25) HGTRY(vcycle25(d_z, d_r, done));
+                        else jacobi_apply_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(plane, K, d_z, d_r, d_dinv);
                         cg_dot_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_r, d_z, d_part1);
                         HGTRY(stage_beta(d_part1, nb_vec, nb_vec, 0));
                         cg_pupdate_kernel<T><<<nb_vec, VEC_THREADS, 0, stream>>>(d_state, plane, K, d_p, d_z);
