@@ -37,7 +37,7 @@ namespace hg {
 
 #define SL_OUT 120        // columns a warp owns
 #define SL_R 64           // rows per chunk
-#define SL_SPB 2          // tasks (warps) per block and channel
+#define SL_WPB 8          // warps per block; a warp serves one (chunk, channel) pair
 
 // activity of the chunks: 0 = no free pixel within the chunk grown by `halo` (skipped), 1 = simple
 // (every pixel the warp reads is hard or a regular interior pixel -- code 0xAA, no soft weight: the
@@ -421,21 +421,21 @@ struct SlLeanUp : SlLean<T> {
 // this lane's slot-0 quad in the warp's shared-memory ring (dynamic shared memory: SL_RING x 128 T per warp)
 template <typename T> __device__ __forceinline__ T* sl_ring() {
     extern __shared__ __align__(16) unsigned char sl_smem[];
-    const int warp = threadIdx.z * blockDim.y + threadIdx.y;
-    return reinterpret_cast<T*>(sl_smem) + (warp * SL_RING * 32 + threadIdx.x) * 4;
+    return reinterpret_cast<T*>(sl_smem) + ((threadIdx.x >> 5) * SL_RING * 32 + (threadIdx.x & 31)) * 4;
 }
 
 // One warp per task (chunk) and channel; `tasks` lists the chunks of one kind (lean or general).
 template <typename T, bool SOFT, bool LEAN>
-__global__ void __launch_bounds__(32 * SL_SPB * 4, LEAN ? (sizeof(T) == 4 ? 4 : 2) : 1)
+__global__ void __launch_bounds__(32 * SL_WPB, LEAN ? (sizeof(T) == 4 ? 4 : 2) : 1)
 sl_down_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict__ r, Coarse<T> cl, const int* __restrict__ tasks,
                int ntasks, int ns, int zero_x, const int* __restrict__ done) {
     if (done && *done) return;
-    const int idx = blockIdx.x * SL_SPB + threadIdx.y, k = blockIdx.y * blockDim.z + threadIdx.z;
-    if (idx >= ntasks || k >= g.K) return;
+    const int wid = blockIdx.x * SL_WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;     // warp <-> (task, channel)
+    const int idx = wid / g.K, k = wid - idx * g.K;
+    if (idx >= ntasks) return;
     const int task = tasks[idx], t = task / ns, s = task - t * ns;
-    const int c0 = s * SL_OUT - 4 + 4 * (int)threadIdx.x;
-    const bool colin = c0 >= 0 && c0 < g.pitch, owner = threadIdx.x >= 1 && threadIdx.x <= 30;
+    const int c0 = s * SL_OUT - 4 + 4 * lane;
+    const bool colin = c0 >= 0 && c0 < g.pitch, owner = lane >= 1 && lane <= 30;
     T wjm[2], wjp[2];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -455,7 +455,7 @@ sl_down_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict_
         f.run();
     } else {
         SlDown<T, SOFT> d;
-        d.lane = threadIdx.x;
+        d.lane = lane;
         d.cx.g = g; d.cx.code = code; d.cx.c0 = c0; d.cx.colin = colin; d.owner = owner;
         d.rk = r + k * g.plane;
         d.cl = cl; d.zero_x = zero_x;
@@ -560,15 +560,16 @@ struct SlUp {
 };
 
 template <typename T, bool SOFT, bool LEAN>
-__global__ void __launch_bounds__(32 * SL_SPB * 4, LEAN ? (sizeof(T) == 4 ? 3 : 1) : 1)
+__global__ void __launch_bounds__(32 * SL_WPB, LEAN ? (sizeof(T) == 4 ? 3 : 1) : 1)
 sl_up_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict__ r, T* __restrict__ z, Coarse<T> cl, int have_coarse,
              const int* __restrict__ tasks, int ntasks, int ns, int nt, double* __restrict__ part_rz, const int* __restrict__ done) {
     if (done && *done) return;
-    const int idx = blockIdx.x * SL_SPB + threadIdx.y, k = blockIdx.y * blockDim.z + threadIdx.z;
-    if (idx >= ntasks || k >= g.K) return;
+    const int wid = blockIdx.x * SL_WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;     // warp <-> (task, channel)
+    const int idx = wid / g.K, k = wid - idx * g.K;
+    if (idx >= ntasks) return;
     const int task = tasks[idx], t = task / ns, s = task - t * ns;
-    const int c0 = s * SL_OUT - 4 + 4 * (int)threadIdx.x;
-    const bool colin = c0 >= 0 && c0 < g.pitch, owner = threadIdx.x >= 1 && threadIdx.x <= 30;
+    const int c0 = s * SL_OUT - 4 + 4 * lane;
+    const bool colin = c0 >= 0 && c0 < g.pitch, owner = lane >= 1 && lane <= 30;
     double acc;
     if (LEAN) {
         SlLeanUp<T> f;
@@ -582,7 +583,7 @@ sl_up_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict__ 
         acc = f.acc;
     } else {
         SlUp<T, SOFT> u;
-        u.lane = threadIdx.x;
+        u.lane = lane;
         u.cx.g = g; u.cx.code = code; u.cx.c0 = c0; u.cx.colin = colin; u.owner = owner;
         u.rk = r + k * g.plane; u.zk = z + k * g.plane;
         u.ek = have_coarse ? cl.x + k * cl.plane : nullptr;
@@ -592,7 +593,96 @@ sl_up_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict__ 
         acc = u.acc;
     }
     const double sdot = warp_sum(acc);
-    if (threadIdx.x == 0) part_rz[(long long)k * ((long long)ns * nt) + task] = sdot;
+    if (lane == 0) part_rz[(long long)k * ((long long)ns * nt) + task] = sdot;
+}
+
+// ---- q = A p (+ p.q), streaming ------------------------------------------------------------------------------
+// The stencil launch of the CG loop in the same style: a warp marches down its chunk with a window of
+// three rows of p in registers, rows arriving through the cp.async ring; every row of p is read once
+// (no re-read of the rows above / below a tile), quads without a free pixel are neither read (p is 0
+// there) nor written, left / right neighbours come by shuffle.  GENERAL: weights decoded from the code
+// bytes (grid borders, cut edges); otherwise every free pixel is a regular interior pixel.  Soft
+// weights and gradient-penalty edges stay with lap_tile_kernel.
+#define SL_LAP_PD 4       // the stencil kernel requests p this many rows ahead
+template <typename T, bool GENERAL>
+struct SlLap : SlLean<T> {
+    using B = SlLean<T>;
+    T* qk;
+    double acc;
+    V4<T> P[8];
+
+    template <int U> __device__ __forceinline__ void step(int ib) {     // ib = i0 (mod 8: 0)
+        constexpr int C = U & 7, CU = (C + 7) & 7, CD = (C + 1) & 7;
+        const int i = ib + U;
+        // code of row i + SL_LAP_PD + 3, request for row i + 1 + SL_LAP_PD, row i + 1 arrives
+        B::M[(C + SL_LAP_PD + 3) & 7] = B::load_code(i + SL_LAP_PD + 3);
+        B::request(i + 1 + SL_LAP_PD, (C + 1 + SL_LAP_PD) & 7, B::M[(C + 1 + SL_LAP_PD) & 7]);
+        sl_cp_wait<SL_LAP_PD>();
+        P[CD] = B::row(CD);
+        const unsigned m = B::M[C];
+        const T lf0 = sl_up1(P[C].v[3]), rt3 = sl_dn1(P[C].v[0]);
+        if (i < B::i0 + SL_R && B::owner && m) {
+            V4<T> out;
+            T part = T(0);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const unsigned cb = (m >> (8 * p)) & 0xffu;
+                const T lf = p == 0 ? lf0 : P[C].v[p - 1], rt = p == 3 ? rt3 : P[C].v[p + 1];
+                T v;
+                if (!GENERAL || cb == 0xAAu || cb == 0u) {
+                    v = cb ? P[C].v[p] - T(0.25) * ((P[CU].v[p] + P[CD].v[p]) + (lf + rt)) : T(0);
+                } else {
+                    T wu, wd, wl, wr;
+                    decode(cb, wu, wd, wl, wr);
+                    v = (wu + wd + wl + wr) * P[C].v[p] - wu * P[CU].v[p] - wd * P[CD].v[p] - wl * lf - wr * rt;
+                }
+                out.v[p] = v;
+                part += P[C].v[p] * v;
+            }
+            acc += (double)part;
+            st4(qk + (long long)i * B::pitch + B::c0, out);
+        }
+    }
+    __device__ __forceinline__ void run() {
+        acc = 0.0;
+        const int i0 = B::i0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { P[q] = zero4<T>(); B::M[q] = 0u; }
+        // codes of rows i0 - 1 .. i0 + SL_LAP_PD + 2 (slots 7, 0, 1, ...), p of rows i0 - 1 .. i0 + SL_LAP_PD
+#pragma unroll
+        for (int q = -1; q < SL_LAP_PD + 3; ++q) B::M[q & 7] = B::load_code(i0 + q);
+#pragma unroll
+        for (int q = -1; q <= SL_LAP_PD; ++q) B::request(i0 + q, q & 7, B::M[q & 7]);
+        sl_cp_wait<SL_LAP_PD>();          // rows i0 - 1 and i0 have landed
+        P[7] = B::row(7);
+        P[0] = B::row(0);
+#pragma unroll 1
+        for (int ib = i0; ib < i0 + SL_R; ib += 8) {
+            step<0>(ib); step<1>(ib); step<2>(ib); step<3>(ib); step<4>(ib); step<5>(ib); step<6>(ib); step<7>(ib);
+        }
+        sl_cp_wait<0>();
+    }
+};
+
+template <typename T, bool GENERAL>
+__global__ void __launch_bounds__(32 * SL_WPB, sizeof(T) == 4 ? 4 : 2)
+sl_lap_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict__ p, T* __restrict__ q, const int* __restrict__ tasks,
+              int ntasks, int ns, int nt, double* __restrict__ part_pq, const int* __restrict__ done) {
+    if (done && *done) return;
+    const int wid = blockIdx.x * SL_WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int idx = wid / g.K, k = wid - idx * g.K;
+    if (idx >= ntasks) return;
+    const int task = tasks[idx], t = task / ns, s = task - t * ns;
+    SlLap<T, GENERAL> f;
+    f.ring = sl_ring<T>();
+    f.code = code; f.rk = p + k * g.plane; f.qk = q + k * g.plane;
+    f.rows = g.rows; f.pitch = g.pitch; f.i0 = t * SL_R;
+    f.c0 = s * SL_OUT - 4 + 4 * lane;
+    f.colin = f.c0 >= 0 && f.c0 < g.pitch;
+    f.owner = lane >= 1 && lane <= 30;
+    f.run();
+    const double sdot = warp_sum(f.acc);
+    if (lane == 0) part_pq[(long long)k * ((long long)ns * nt) + task] = sdot;
 }
 
 }  // namespace hg

@@ -181,6 +181,7 @@ struct Solver : SolverBase {
     // streaming legs (fine_stream.cuh): chunk activity (halo 0 / halo 1) and per-chunk partial sums of r.z
     uint8_t *d_sl_up = nullptr, *d_sl_down = nullptr;
     double* d_spart = nullptr;
+    double* d_spart2 = nullptr;        // per-chunk partial sums of p.q (streaming stencil kernel)
     int sl_ns = 0, sl_nt = 0;
     int* d_sl_tasks = nullptr;
     int sl_off[4] = {0, 0, 0, 0}, sl_n_down_lean = 0, sl_n_down_gen = 0, sl_n_up_lean = 0, sl_n_up_gen = 0;
@@ -205,7 +206,7 @@ struct Solver : SolverBase {
         if (kRefine) { cudaFree(d_xm); cudaFree(d_bm); }
         cudaFree(d_tile_active); cudaFree(d_tpart0); cudaFree(d_tpart1);
         cudaFree(d_down_active); cudaFree(d_code); cudaFree(d_lpart);
-        cudaFree(d_sl_up); cudaFree(d_sl_down); cudaFree(d_spart); cudaFree(d_sl_tasks);
+        cudaFree(d_sl_up); cudaFree(d_sl_down); cudaFree(d_spart); cudaFree(d_spart2); cudaFree(d_sl_tasks);
         if (comm && g_nccl.ok) g_nccl.CommDestroy(comm);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -610,6 +611,10 @@ struct Solver : SolverBase {
         CU(cudaMalloc(&d_sl_down, (size_t)sl_ns * sl_nt));
         CU(cudaMalloc(&d_spart, (size_t)sl_ns * sl_nt * K * sizeof(double)));
         CU(cudaMemsetAsync(d_spart, 0, (size_t)sl_ns * sl_nt * K * sizeof(double), stream));
+        cudaFree(d_spart2);
+        d_spart2 = nullptr;
+        CU(cudaMalloc(&d_spart2, (size_t)sl_ns * sl_nt * K * sizeof(double)));
+        CU(cudaMemsetAsync(d_spart2, 0, (size_t)sl_ns * sl_nt * K * sizeof(double), stream));
         sl_activity_kernel<<<dim3(sl_ns, sl_nt), 256, 0, stream>>>(d_flags, d_code, rows, cols, pitch, 0, sl_ns, d_sl_up);
         sl_activity_kernel<<<dim3(sl_ns, sl_nt), 256, 0, stream>>>(d_flags, d_code, rows, cols, pitch, 1, sl_ns, d_sl_down);
         {   // task lists: [down lean | down general | up lean | up general], in row-major chunk order
@@ -639,8 +644,10 @@ struct Solver : SolverBase {
         CU(cudaFuncSetAttribute(mg_down0_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, DOWN_H, true>)));
         CU(cudaFuncSetAttribute(mg_up0_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, UP_H, false>)));
         CU(cudaFuncSetAttribute(mg_up0_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, UP_H, true>)));
-        CU(cudaFuncSetAttribute(sl_down_kernel<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_SPB * 4 * SL_RING * 128 * sizeof(T))));
-        CU(cudaFuncSetAttribute(sl_up_kernel<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_SPB * 4 * SL_RING * 128 * sizeof(T))));
+        CU(cudaFuncSetAttribute(sl_down_kernel<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_WPB * SL_RING * 128 * sizeof(T))));
+        CU(cudaFuncSetAttribute(sl_up_kernel<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_WPB * SL_RING * 128 * sizeof(T))));
+        CU(cudaFuncSetAttribute(sl_lap_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_WPB * SL_RING * 128 * sizeof(T))));
+        CU(cudaFuncSetAttribute(sl_lap_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_WPB * SL_RING * 128 * sizeof(T))));
         CU(cudaFuncSetAttribute(mg_down0v_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VRegionSmem<T>)));
         CU(cudaFuncSetAttribute(mg_up0v_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VRegionSmem<T>)));
         return HG_OK;
@@ -769,9 +776,9 @@ struct Solver : SolverBase {
     // the streaming legs serve every configuration without gradient-penalty edges
     bool stream_legs() const { return !has_pen && !tile_legs && !scalar_legs; }
     bool has_soft() const { return d_soft != nullptr || soft_scalar != 0.0; }
-    dim3 sl_grid(int ntasks) const { return dim3((ntasks + SL_SPB - 1) / SL_SPB, (K + 3) / 4); }
-    dim3 sl_block() const { return dim3(32, SL_SPB, std::min(K, 4)); }
-    size_t sl_smem() const { return (size_t)SL_SPB * std::min(K, 4) * SL_RING * 128 * sizeof(T); }   // lean kernels: one ring of r rows per warp
+    dim3 sl_grid(int ntasks) const { return dim3((unsigned)(((long long)ntasks * K + SL_WPB - 1) / SL_WPB)); }
+    dim3 sl_block() const { return dim3(32 * SL_WPB); }
+    size_t sl_smem() const { return (size_t)SL_WPB * SL_RING * 128 * sizeof(T); }   // lean kernels: one ring of rows per warp
     void launch_sl_down(const Grid<T>& g, const T* r, const Coarse<T>& c1, const int* done) {
         const int zx = unfused_coarse ? 1 : 0;
         if (sl_n_down_lean)
@@ -790,6 +797,26 @@ struct Solver : SolverBase {
             else sl_up_kernel<T, false, false><<<sl_grid(sl_n_up_gen), sl_block(), 0, stream>>>(g, d_code, r, z, c1, have_coarse, d_sl_tasks + sl_off[3], sl_n_up_gen, sl_ns, sl_nt, d_spart, done);
         }
         launches += (sl_n_up_lean > 0) + (sl_n_up_gen > 0) - 1;
+    }
+    // q = A p with the streaming kernel (no soft weights, no gradient-penalty edges), partial sums of p.q per chunk
+    bool stream_lap() const { return stream_legs() && !has_soft() && !getenv("HGRID_TILE_LAP"); }
+    void launch_sl_lap(const T* p, T* q, const int* done) {
+        const Grid<T> g = grid();
+        if (sl_n_up_lean)
+            sl_lap_kernel<T, false><<<sl_grid(sl_n_up_lean), sl_block(), sl_smem(), stream>>>(g, d_code, p, q, d_sl_tasks + sl_off[2], sl_n_up_lean, sl_ns, sl_nt, d_spart2, done);
+        if (sl_n_up_gen)
+            sl_lap_kernel<T, true><<<sl_grid(sl_n_up_gen), sl_block(), sl_smem(), stream>>>(g, d_code, p, q, d_sl_tasks + sl_off[3], sl_n_up_gen, sl_ns, sl_nt, d_spart2, done);
+        launches += (sl_n_up_lean > 0) + (sl_n_up_gen > 0);
+    }
+    // the stencil launch of the CG loop + the scalar stage that forms alpha
+    int lap_and_alpha(const T* p, T* q, const int* done) {
+        if (stream_lap()) {
+            launch_sl_lap(p, q, done);
+            const int t0 = ghost_top / SL_R, t1 = ghost_bottom ? (rows - ghost_bottom) / SL_R : sl_nt;
+            return stage_alpha(d_spart2 + (long long)t0 * sl_ns, (t1 - t0) * sl_ns, (long long)sl_ns * sl_nt);
+        }
+        launch_lap_tile<T, 0, 1>(p, nullptr, q, d_lpart, done);
+        return stage_alpha(lap_part(d_lpart), n_own_lap(), n_lap());
     }
     // scalar stage after the V-cycle: r.z from the partial sums the upward leg left (owned rows only)
     int stage_beta_rz(int init) {
@@ -1176,9 +1203,8 @@ struct Solver : SolverBase {
                 for (int s = 0; s < batch; ++s) {
                     if (mg) {
                         HGTRY(exchange(d_p, 1));
-                        launch_lap_tile<T, 0, 1>(d_p, nullptr, d_q, d_lpart, done);
-                        HGTRY(stage_alpha(lap_part(d_lpart), n_own_lap(), n_lap()));
-                        --launches;
+                        HGTRY(lap_and_alpha(d_p, d_q, done));
+                        launches -= 2;
                         cg_update_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, e, d_r, d_p, d_q, d_tile_active, d_tpart0);
                         HGTRY(stage_check(tile_part(d_tpart0), n_own_tiles(), nt));
                         HGTRY(vcycle(d_z, d_r, done, d_tpart1));
@@ -1308,7 +1334,8 @@ struct Solver : SolverBase {
         if (iters <= 0) iters = 1;
         // the launch the CG loop itself makes: q = A p with the partial sums of p.q (tile path), or the flat operator
         auto one = [&]() {
-            if (use_mg()) launch_lap_tile<T, 0, 1>(d_p, nullptr, d_q, d_lpart, nullptr);
+            if (use_mg() && stream_lap()) launch_sl_lap(d_p, d_q, nullptr);
+            else if (use_mg()) launch_lap_tile<T, 0, 1>(d_p, nullptr, d_q, d_lpart, nullptr);
             else launch_op<0, 1>(d_p, nullptr, d_q, d_part0, nullptr);
         };
         for (int w = 0; w < 3; ++w) one();
