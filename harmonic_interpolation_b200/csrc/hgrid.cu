@@ -727,7 +727,38 @@ struct Solver : SolverBase {
     // z = M^-1 r : one V(1,1) cycle from a zero initial guess; also leaves the per-tile partial
     // sums of r.z in part_rz.  Level 0 is two fused tile kernels (fine.cuh).  In slab mode the
     // ghost bands are refreshed once per level and leg and levels >= HG_GATHER_LEVEL run replicated.
+    // Experiment aid (HGRID_GENERIC_VCYCLE=nu): a V(nu,nu) cycle assembled from the separate, unfused kernels
+    // of mg.cuh on every level -- slow, but any nu; used to measure what more smoothing buys in iterations.
+    int generic_nu = getenv("HGRID_GENERIC_VCYCLE") ? atoi(getenv("HGRID_GENERIC_VCYCLE")) : 0;
+    int vcycle_generic(T* z, T* r, const int* done) {
+        const Grid<T> g = grid();
+        FineAcc<T> fa{g};
+        const int nl = (int)coarse.size(), nu = generic_nu;
+        CU(cudaMemsetAsync(z, 0, (size_t)plane * K * sizeof(T), stream));
+        dim3 rb((cols / 2 + 1 + 255) / 256, rows);
+        for (int s = 0; s < nu; ++s)
+            for (int c = 0; c < 2; ++c) rbgs0_kernel<T><<<rb, 256, 0, stream>>>(fa, z, r, c, done);
+        if (nl > 0) {
+            resid_restrict_kernel<T, FineAcc<T>><<<dim3((coarse[0].pitch + 255) / 256, coarse[0].rows), 256, 0, stream>>>(fa, z, r, coarse[0], K, done);
+            for (int l = 0; l + 1 < nl; ++l) {
+                for (int s = 0; s < nu; ++s) coarse_pre(coarse[l], done);
+                coarse_restrict(coarse[l], coarse[l + 1], done);
+            }
+            coarse_solve(coarse[nl - 1], d_dense, done);
+            for (int l = nl - 2; l >= 0; --l) {
+                coarse_prolong(coarse[l], coarse[l + 1], done);
+                for (int s = 0; s < nu; ++s) coarse_post(coarse[l], done);
+            }
+            prolong_add_kernel<T, FineAcc<T>><<<dim3((cols + 255) / 256, rows), 256, 0, stream>>>(fa, z, coarse[0], K, done);
+        }
+        for (int s = 0; s < nu; ++s)
+            for (int c = 1; c >= 0; --c) rbgs0_kernel<T><<<rb, 256, 0, stream>>>(fa, z, r, c, done);
+        cg_dot_kernel<T><<<vec_blocks(), VEC_THREADS, 0, stream>>>(nullptr, plane, K, r, z, d_part1);
+        return HG_OK;
+    }
+
     int vcycle(T* z, T* r, const int* done, double* part_rz) {
+        if (generic_nu > 0 && world == 1) return vcycle_generic(z, r, done);
         const Grid<T> g = grid();
         const int nl = (int)coarse.size();
         if (nl > 0) {
@@ -820,6 +851,7 @@ struct Solver : SolverBase {
     }
     // scalar stage after the V-cycle: r.z from the partial sums the upward leg left (owned rows only)
     int stage_beta_rz(int init) {
+        if (generic_nu > 0 && world == 1) return stage_beta(d_part1, vec_blocks(), vec_blocks(), init);
         if (stream_legs()) {
             const int t0 = ghost_top / SL_R, t1 = ghost_bottom ? (rows - ghost_bottom) / SL_R : sl_nt;
             return stage_beta(d_spart + (long long)t0 * sl_ns, (t1 - t0) * sl_ns, (long long)sl_ns * sl_nt, init);
