@@ -254,11 +254,12 @@ struct SlLean {
     V4<T> Z[8];
     unsigned M[8];
     __device__ __forceinline__ unsigned load_code(int i) const {
-        return (colin && i >= 0 && i < rows) ? *reinterpret_cast<const unsigned*>(code + (long long)i * pitch + c0) : 0u;
+        // (32-bit element offsets on the lean paths: the host only takes them when rows * pitch < 2^31)
+        return (colin && (unsigned)i < (unsigned)rows) ? *reinterpret_cast<const unsigned*>(code + (i * pitch + c0)) : 0u;
     }
     // request row i of r into slot `slot` (zeros where the quad has no free pixel); one commit group per row
     __device__ __forceinline__ void request(int i, int slot, unsigned m) {
-        const T* src = m ? rk + (long long)i * pitch + c0 : rk;
+        const T* src = rk + (m ? i * pitch + c0 : 0);
         T* dst = ring + slot * 128;
         sl_cp16(dst, src, m != 0u);
         if (sizeof(T) == 8) sl_cp16(dst + 2, src + 2, m != 0u);
@@ -341,7 +342,7 @@ struct SlLeanDown : SlLean<T> {
                     const T va = S[C3].v[0] + wim * (wjm[0] * upL + wjp[0] * S[C4].v[1]) + wip * (wjm[0] * dnL + wjp[0] * S[C2].v[1]);
                     T vb = S[C3].v[2] + wim * (wjm[1] * S[C4].v[1] + wjp[1] * S[C4].v[3]) + wip * (wjm[1] * S[C2].v[1] + wjp[1] * S[C2].v[3]);
                     if (Ja + 1 >= ccols) vb = T(0);
-                    const long long oc = (long long)I * cpitch + Ja;
+                    const int oc = I * cpitch + Ja;
                     if (*reinterpret_cast<const unsigned short*>(ccode + oc)) {
                         sts2(bk + oc, va, vb);
                         if (zero_x) sts2(xk + oc, T(0), T(0));
@@ -376,7 +377,7 @@ struct SlLeanUp : SlLean<T> {
         if (ek) {
             const int Ic = min(max(I, 0), crows - 1);
             const int J0 = min(max(B::c0 >> 1, 0), ccols - 1), J1 = min(max((B::c0 >> 1) + 1, 0), ccols - 1);
-            const T* row = ek + (long long)Ic * cpitch;
+            const T* row = ek + Ic * cpitch;
             a = row[J0]; b = row[J1];
         }
         E[SLOT][0] = a; E[SLOT][1] = b;
@@ -402,7 +403,7 @@ struct SlLeanUp : SlLean<T> {
         if (io >= B::i0 && io < B::i0 + SL_R && B::owner && B::M[C2]) {
 #pragma unroll
             for (int p = 0; p < 4; ++p) acc += (double)(B::Z[C2].v[p] * r2.v[p]);
-            st4(zk + (long long)io * B::pitch + B::c0, B::Z[C2]);
+            st4(zk + (io * B::pitch + B::c0), B::Z[C2]);
         }
     }
     __device__ __forceinline__ void run() {
@@ -640,7 +641,7 @@ struct SlLap : SlLean<T> {
                 part += P[C].v[p] * v;
             }
             acc += (double)part;
-            st4(qk + (long long)i * B::pitch + B::c0, out);
+            st4(qk + (i * B::pitch + B::c0), out);
         }
     }
     __device__ __forceinline__ void run() {

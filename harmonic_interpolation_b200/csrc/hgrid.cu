@@ -805,7 +805,7 @@ struct Solver : SolverBase {
     }
 
     // the streaming legs serve every configuration without gradient-penalty edges
-    bool stream_legs() const { return !has_pen && !tile_legs && !scalar_legs; }
+    bool stream_legs() const { return !has_pen && !tile_legs && !scalar_legs && plane < (1LL << 31) - (1LL << 20); }   // 32-bit offsets on the lean paths
     bool has_soft() const { return d_soft != nullptr || soft_scalar != 0.0; }
     dim3 sl_grid(int ntasks) const { return dim3((unsigned)(((long long)ntasks * K + SL_WPB - 1) / SL_WPB)); }
     dim3 sl_block() const { return dim3(32 * SL_WPB); }
