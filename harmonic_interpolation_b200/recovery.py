@@ -499,6 +499,8 @@ def convert_grid_normal_constraints_to_dx_and_dy_constraints(rows, cols, normal_
     dy = -n.y/n.z on edge (i,j)-(i,j+1).  Constraints in the last row / column are shifted
     globally by one if the first row / column is empty, else locally if the slot is free."""
     assert rows > 0 and cols > 0
+    if _is_array_form(normal_constraints):
+        return _convert_normals_arrays(rows, cols, *normal_constraints)
     all_is = set(i for i, j, n in normal_constraints)
     all_js = set(j for i, j, n in normal_constraints)
     if (rows - 1) in all_is and 0 not in all_is:
@@ -527,6 +529,42 @@ def convert_grid_normal_constraints_to_dx_and_dy_constraints(rows, cols, normal_
         dx_constraints.append((i, j, -n[0] / n[2]))
         dy_constraints.append((i, j, -n[1] / n[2]))
     return dx_constraints, dy_constraints
+
+
+def _convert_normals_arrays(rows, cols, ij, normals):
+    """Array form of convert_grid_normal_constraints_to_dx_and_dy_constraints (extension): ij (n,2) integer
+    pixels, normals (n,3); returns ((ij, dx values), (ij, dy values)) in the array form solve_grid_linear accepts.
+    Same rules as the tuple form: global shift by one if the last row / column is used and the first is
+    not; a constraint in the last row / column moves one pixel inwards unless that slot is taken."""
+    ij = np.asarray(ij, np.int64).reshape(-1, 2).copy()
+    n = np.asarray(normals, float).reshape(-1, 3)
+    assert len(ij) == len(n)
+    if len(ij) and (ij[:, 0] == rows - 1).any() and not (ij[:, 0] == 0).any():
+        ij[:, 0] -= 1
+    if len(ij) and (ij[:, 1] == cols - 1).any() and not (ij[:, 1] == 0).any():
+        ij[:, 1] -= 1
+    safe = (ij[:, 0] < rows - 1) & (ij[:, 1] < cols - 1)
+    key = ij[:, 0] * cols + ij[:, 1]
+    # later duplicates of a safe pixel overwrite earlier ones (dict semantics)
+    ks, first_of_rev = np.unique(key[safe][::-1], return_index=True)
+    idx_safe = np.flatnonzero(safe)[::-1][first_of_rev]
+    taken = set(ks.tolist())
+    extra = []
+    for q in np.flatnonzero(~safe):          # few: only the last row / column
+        i, j = ij[q]
+        t = (i - (i == rows - 1)) * cols + (j - (j == cols - 1))
+        if t not in taken:
+            taken.add(int(t))
+            extra.append((int(t), q))
+    keys = np.concatenate([ks, np.asarray([t for t, q in extra], np.int64)]) if extra else ks
+    src = np.concatenate([idx_safe, np.asarray([q for t, q in extra], np.int64)]) if extra else idx_safe
+    nn = n[src]
+    ok = nn[:, 2] >= 1e-5
+    if not ok.all():
+        print('Silhouette normal!  TODO: Make it a height map discontinuity.  Skipping for now...')
+    keys, nn = keys[ok], nn[ok]
+    out_ij = np.stack([keys // cols, keys % cols], axis=1)
+    return (out_ij, -nn[:, 0] / nn[:, 2]), (out_ij, -nn[:, 1] / nn[:, 2])
 
 
 def normalize_to_char_img(img):

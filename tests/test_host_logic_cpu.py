@@ -1,0 +1,31 @@
+"""CPU: host-side logic of the drop-in modules that needs no GPU (array forms of the constraint encoders)."""
+import numpy as np
+
+from harmonic_interpolation_b200 import recovery as R
+
+
+def test_normals_conversion_array_form_matches_tuple_form():
+    """recovery.py:1532-1620 (tuple form) against the vectorised array form, including the global shift,
+    constraints in the last row / column, and duplicates."""
+    rng = np.random.default_rng(0)
+    for rows, cols in ((9, 7), (12, 12), (2, 30)):
+        for trial in range(24):
+            m = int(rng.integers(3, 30))
+            ij = np.stack([rng.integers(trial % 2, rows, m), rng.integers((trial // 2) % 2, cols, m)], 1)
+            nrm = rng.normal(size=(m, 3))
+            nrm[:, 2] = np.abs(nrm[:, 2]) + 0.1
+            tup = [(int(i), int(j), tuple(v)) for (i, j), v in zip(ij, nrm)]
+            dx, dy = R.convert_grid_normal_constraints_to_dx_and_dy_constraints(rows, cols, tup)
+            (aij, adx), (bij, ady) = R.convert_grid_normal_constraints_to_dx_and_dy_constraints(rows, cols, (ij, nrm))
+            assert sorted((i, j, round(v, 12)) for i, j, v in dx) == sorted((int(i), int(j), round(float(v), 12)) for (i, j), v in zip(aij, adx))
+            assert sorted((i, j, round(v, 12)) for i, j, v in dy) == sorted((int(i), int(j), round(float(v), 12)) for (i, j), v in zip(bij, ady))
+
+
+def test_cut_planes_match_cut_edges_from_mask():
+    rng = np.random.default_rng(1)
+    mask = rng.random((13, 17)) < 0.4
+    cd, cr = R.cut_planes_from_mask(mask)
+    edges = R.cut_edges_from_mask(mask)
+    cd2, cr2, n = R._cut_planes(13, 17, edges)
+    assert n == len(edges) == int(cd.sum() + cr.sum())
+    assert (cd == cd2).all() and (cr == cr2).all()
