@@ -604,41 +604,52 @@ sl_up_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict__ 
 // there) nor written, left / right neighbours come by shuffle.  GENERAL: weights decoded from the code
 // bytes (grid borders, cut edges); otherwise every free pixel is a regular interior pixel.  Soft
 // weights and gradient-penalty edges stay with lap_tile_kernel.
-#define SL_LAP_PD 4       // the stencil kernel requests p this many rows ahead
-template <typename T, bool GENERAL>
-struct SlLap : SlLean<T> {
-    using B = SlLean<T>;
-    T* qk;
+// MODE 0: q = A p, partial sums of p.q  (p is 0 at hard pixels: quads without a free pixel are not read).
+// MODE 1: r = -A x, partial sums of r.r  (the true residual of a system whose right-hand side is zero --
+//         hard constraints only; x carries the hard values, so a quad is read whenever it or a
+//         neighbouring quad holds a free pixel).  TX is the operand type (double for the master
+//         iterate of the fp32 mode), TO the result type.
+template <typename TX, typename TO, bool GENERAL, int MODE>
+struct SlLap : SlLean<TX> {
+    using B = SlLean<TX>;
+    static constexpr int PD = MODE ? 3 : 4;     // rows requested ahead
+    TO* qk;
     double acc;
-    V4<T> P[8];
+    V4<TX> P[8];
 
+    // does the lane's quad of a row matter, given the code words of the row above, the row itself, the row below?
+    __device__ __forceinline__ unsigned need(unsigned up, unsigned mid, unsigned dn) const {
+        if (MODE == 0) return mid;
+        return up | mid | dn | sl_up1(mid >> 24) | sl_dn1(mid & 0xffu);
+    }
     template <int U> __device__ __forceinline__ void step(int ib) {     // ib = i0 (mod 8: 0)
         constexpr int C = U & 7, CU = (C + 7) & 7, CD = (C + 1) & 7;
         const int i = ib + U;
-        // code of row i + SL_LAP_PD + 3, request for row i + 1 + SL_LAP_PD, row i + 1 arrives
-        B::M[(C + SL_LAP_PD + 3) & 7] = B::load_code(i + SL_LAP_PD + 3);
-        B::request(i + 1 + SL_LAP_PD, (C + 1 + SL_LAP_PD) & 7, B::M[(C + 1 + SL_LAP_PD) & 7]);
-        sl_cp_wait<SL_LAP_PD>();
+        // code of row i + PD + 3, request for row i + 1 + PD, row i + 1 arrives
+        B::M[(C + PD + 3) & 7] = B::load_code(i + PD + 3);
+        B::request(i + 1 + PD, (C + 1 + PD) & 7, need(B::M[(C + PD) & 7], B::M[(C + 1 + PD) & 7], B::M[(C + 2 + PD) & 7]));
+        sl_cp_wait<PD>();
         P[CD] = B::row(CD);
         const unsigned m = B::M[C];
-        const T lf0 = sl_up1(P[C].v[3]), rt3 = sl_dn1(P[C].v[0]);
+        const TX lf0 = sl_up1(P[C].v[3]), rt3 = sl_dn1(P[C].v[0]);
         if (i < B::i0 + SL_R && B::owner && m) {
-            V4<T> out;
-            T part = T(0);
+            V4<TO> out;
+            TX part = TX(0);
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
                 const unsigned cb = (m >> (8 * p)) & 0xffu;
-                const T lf = p == 0 ? lf0 : P[C].v[p - 1], rt = p == 3 ? rt3 : P[C].v[p + 1];
-                T v;
+                const TX lf = p == 0 ? lf0 : P[C].v[p - 1], rt = p == 3 ? rt3 : P[C].v[p + 1];
+                TX v;
                 if (!GENERAL || cb == 0xAAu || cb == 0u) {
-                    v = cb ? P[C].v[p] - T(0.25) * ((P[CU].v[p] + P[CD].v[p]) + (lf + rt)) : T(0);
+                    v = cb ? P[C].v[p] - TX(0.25) * ((P[CU].v[p] + P[CD].v[p]) + (lf + rt)) : TX(0);
                 } else {
-                    T wu, wd, wl, wr;
+                    TX wu, wd, wl, wr;
                     decode(cb, wu, wd, wl, wr);
                     v = (wu + wd + wl + wr) * P[C].v[p] - wu * P[CU].v[p] - wd * P[CD].v[p] - wl * lf - wr * rt;
                 }
-                out.v[p] = v;
-                part += P[C].v[p] * v;
+                if (MODE == 1) v = -v;
+                out.v[p] = (TO)v;
+                part += (MODE == 0 ? P[C].v[p] : v) * v;
             }
             acc += (double)part;
             st4(qk + (i * B::pitch + B::c0), out);
@@ -648,13 +659,16 @@ struct SlLap : SlLean<T> {
         acc = 0.0;
         const int i0 = B::i0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { P[q] = zero4<T>(); B::M[q] = 0u; }
-        // codes of rows i0 - 1 .. i0 + SL_LAP_PD + 2 (slots 7, 0, 1, ...), p of rows i0 - 1 .. i0 + SL_LAP_PD
+        for (int q = 0; q < 8; ++q) { P[q] = zero4<TX>(); B::M[q] = 0u; }
+        // codes of rows i0 - 2 .. i0 + PD + 2; the ring keeps rows i0 - 1 .. (slots 7, 0, 1, ...); operand rows i0 - 1 .. i0 + PD
+        unsigned cc[PD + 5];
 #pragma unroll
-        for (int q = -1; q < SL_LAP_PD + 3; ++q) B::M[q & 7] = B::load_code(i0 + q);
+        for (int q = 0; q < PD + 5; ++q) cc[q] = B::load_code(i0 - 2 + q);
 #pragma unroll
-        for (int q = -1; q <= SL_LAP_PD; ++q) B::request(i0 + q, q & 7, B::M[q & 7]);
-        sl_cp_wait<SL_LAP_PD>();          // rows i0 - 1 and i0 have landed
+        for (int q = -1; q < PD + 3; ++q) B::M[q & 7] = cc[q + 2];
+#pragma unroll
+        for (int q = -1; q <= PD; ++q) B::request(i0 + q, q & 7, need(cc[q + 1], cc[q + 2], cc[q + 3]));
+        sl_cp_wait<PD>();          // rows i0 - 1 and i0 have landed
         P[7] = B::row(7);
         P[0] = B::row(0);
 #pragma unroll 1
@@ -665,17 +679,17 @@ struct SlLap : SlLean<T> {
     }
 };
 
-template <typename T, bool GENERAL>
-__global__ void __launch_bounds__(32 * SL_WPB, sizeof(T) == 4 ? 4 : 2)
-sl_lap_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict__ p, T* __restrict__ q, const int* __restrict__ tasks,
+template <typename TX, typename TO, bool GENERAL, int MODE>
+__global__ void __launch_bounds__(32 * SL_WPB, sizeof(TX) == 4 ? 4 : 2)
+sl_lap_kernel(Grid<TO> g, const uint8_t* __restrict__ code, const TX* __restrict__ p, TO* __restrict__ q, const int* __restrict__ tasks,
               int ntasks, int ns, int nt, double* __restrict__ part_pq, const int* __restrict__ done) {
     if (done && *done) return;
     const int wid = blockIdx.x * SL_WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int idx = wid / g.K, k = wid - idx * g.K;
     if (idx >= ntasks) return;
     const int task = tasks[idx], t = task / ns, s = task - t * ns;
-    SlLap<T, GENERAL> f;
-    f.ring = sl_ring<T>();
+    SlLap<TX, TO, GENERAL, MODE> f;
+    f.ring = sl_ring<TX>();
     f.code = code; f.rk = p + k * g.plane; f.qk = q + k * g.plane;
     f.rows = g.rows; f.pitch = g.pitch; f.i0 = t * SL_R;
     f.c0 = s * SL_OUT - 4 + 4 * lane;

@@ -646,8 +646,10 @@ struct Solver : SolverBase {
         CU(cudaFuncSetAttribute(mg_up0_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, UP_H, true>)));
         CU(cudaFuncSetAttribute(sl_down_kernel<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_WPB * SL_RING * 128 * sizeof(T))));
         CU(cudaFuncSetAttribute(sl_up_kernel<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_WPB * SL_RING * 128 * sizeof(T))));
-        CU(cudaFuncSetAttribute(sl_lap_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_WPB * SL_RING * 128 * sizeof(T))));
-        CU(cudaFuncSetAttribute(sl_lap_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_WPB * SL_RING * 128 * sizeof(T))));
+        CU(cudaFuncSetAttribute(sl_lap_kernel<T, T, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_WPB * SL_RING * 128 * sizeof(T))));
+        CU(cudaFuncSetAttribute(sl_lap_kernel<T, T, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_WPB * SL_RING * 128 * sizeof(T))));
+        CU(cudaFuncSetAttribute(sl_lap_kernel<double, T, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_WPB * SL_RING * 128 * sizeof(double))));
+        CU(cudaFuncSetAttribute(sl_lap_kernel<double, T, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SL_WPB * SL_RING * 128 * sizeof(double))));
         CU(cudaFuncSetAttribute(mg_down0v_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VRegionSmem<T>)));
         CU(cudaFuncSetAttribute(mg_up0v_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VRegionSmem<T>)));
         return HG_OK;
@@ -834,9 +836,19 @@ struct Solver : SolverBase {
     void launch_sl_lap(const T* p, T* q, const int* done) {
         const Grid<T> g = grid();
         if (sl_n_up_lean)
-            sl_lap_kernel<T, false><<<sl_grid(sl_n_up_lean), sl_block(), sl_smem(), stream>>>(g, d_code, p, q, d_sl_tasks + sl_off[2], sl_n_up_lean, sl_ns, sl_nt, d_spart2, done);
+            sl_lap_kernel<T, T, false, 0><<<sl_grid(sl_n_up_lean), sl_block(), sl_smem(), stream>>>(g, d_code, p, q, d_sl_tasks + sl_off[2], sl_n_up_lean, sl_ns, sl_nt, d_spart2, done);
         if (sl_n_up_gen)
-            sl_lap_kernel<T, true><<<sl_grid(sl_n_up_gen), sl_block(), sl_smem(), stream>>>(g, d_code, p, q, d_sl_tasks + sl_off[3], sl_n_up_gen, sl_ns, sl_nt, d_spart2, done);
+            sl_lap_kernel<T, T, true, 0><<<sl_grid(sl_n_up_gen), sl_block(), sl_smem(), stream>>>(g, d_code, p, q, d_sl_tasks + sl_off[3], sl_n_up_gen, sl_ns, sl_nt, d_spart2, done);
+        launches += (sl_n_up_lean > 0) + (sl_n_up_gen > 0);
+    }
+    // r = -A x from the fp64 master iterate (the true residual when the right-hand side is zero), partial sums of r.r
+    void launch_sl_resid(const double* x, T* r) {
+        const Grid<T> g = grid();
+        const size_t sm = (size_t)SL_WPB * SL_RING * 128 * sizeof(double);
+        if (sl_n_up_lean)
+            sl_lap_kernel<double, T, false, 1><<<sl_grid(sl_n_up_lean), sl_block(), sm, stream>>>(g, d_code, x, r, d_sl_tasks + sl_off[2], sl_n_up_lean, sl_ns, sl_nt, d_spart2, nullptr);
+        if (sl_n_up_gen)
+            sl_lap_kernel<double, T, true, 1><<<sl_grid(sl_n_up_gen), sl_block(), sm, stream>>>(g, d_code, x, r, d_sl_tasks + sl_off[3], sl_n_up_gen, sl_ns, sl_nt, d_spart2, nullptr);
         launches += (sl_n_up_lean > 0) + (sl_n_up_gen > 0);
     }
     // the stencil launch of the CG loop + the scalar stage that forms alpha
@@ -1197,9 +1209,16 @@ struct Solver : SolverBase {
             if (mg) {
                 // master-precision residual with the tile kernel (x, b in fp64 even in fp32 mode)
                 HGTRY(exchange(d_xm, 1));
-                launch_lap_tile<double, 1, 2>(d_xm, b_is_zero ? nullptr : d_bm, d_r, d_lpart, nullptr);
-                HGTRY(stage_outer(lap_part(d_lpart), n_own_lap(), n_lap(), outer == 0, inner_red * inner_red));
-                --launches;
+                if (stream_lap() && b_is_zero) {
+                    launch_sl_resid(d_xm, d_r);
+                    const int t0 = ghost_top / SL_R, t1 = ghost_bottom ? (rows - ghost_bottom) / SL_R : sl_nt;
+                    HGTRY(stage_outer(d_spart2 + (long long)t0 * sl_ns, (t1 - t0) * sl_ns, (long long)sl_ns * sl_nt, outer == 0, inner_red * inner_red));
+                    launches -= 2;
+                } else {
+                    launch_lap_tile<double, 1, 2>(d_xm, b_is_zero ? nullptr : d_bm, d_r, d_lpart, nullptr);
+                    HGTRY(stage_outer(lap_part(d_lpart), n_own_lap(), n_lap(), outer == 0, inner_red * inner_red));
+                    --launches;
+                }
             } else if (kRefine) {
                 resid_master_kernel<T><<<pg, 256, 0, stream>>>(g, op == HG_OP_BILAPLACIAN, d_xm, d_bm, d_r, d_part0);
                 HGTRY(stage_outer(d_part0, nb_res, nb_res, outer == 0, inner_red * inner_red));
