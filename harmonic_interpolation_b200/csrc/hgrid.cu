@@ -182,6 +182,11 @@ struct Solver : SolverBase {
     uint8_t *d_sl_up = nullptr, *d_sl_down = nullptr;
     double* d_spart = nullptr;
     double* d_spart2 = nullptr;        // per-chunk partial sums of p.q (streaming stencil kernel)
+    // fused CG loop: second buffers of p and r (the streaming kernels recompute halo pixels from the old vector),
+    // per-chunk partial sums of r.r
+    T *d_p2 = nullptr, *d_r2 = nullptr;
+    double* d_spart3 = nullptr;
+    bool no_fuse = getenv("HGRID_NO_FUSE") != nullptr;
     int sl_ns = 0, sl_nt = 0;
     int* d_sl_tasks = nullptr;
     int sl_off[4] = {0, 0, 0, 0}, sl_n_down_lean = 0, sl_n_down_gen = 0, sl_n_up_lean = 0, sl_n_up_gen = 0;
@@ -207,6 +212,7 @@ struct Solver : SolverBase {
         cudaFree(d_tile_active); cudaFree(d_tpart0); cudaFree(d_tpart1);
         cudaFree(d_down_active); cudaFree(d_code); cudaFree(d_lpart);
         cudaFree(d_sl_up); cudaFree(d_sl_down); cudaFree(d_spart); cudaFree(d_spart2); cudaFree(d_sl_tasks);
+        cudaFree(d_p2); cudaFree(d_r2); cudaFree(d_spart3);
         if (comm && g_nccl.ok) g_nccl.CommDestroy(comm);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -759,13 +765,18 @@ struct Solver : SolverBase {
         return HG_OK;
     }
 
-    int vcycle(T* z, T* r, const int* done, double* part_rz) {
+    // fuse_r_old != nullptr: the downward leg also forms r = fuse_r_old - alpha q (CG update) and the convergence
+    // check runs right after it, so that the rest of the cycle turns into no-ops once the tolerance is met
+    int vcycle(T* z, T* r, const int* done, double* part_rz, const T* fuse_r_old = nullptr) {
         if (generic_nu > 0 && world == 1) return vcycle_generic(z, r, done);
         const Grid<T> g = grid();
         const int nl = (int)coarse.size();
         if (nl > 0) {
             if (world > 1) HGTRY(exchange(r, HG_GHOST_ROWS));
-            if (stream_legs()) launch_sl_down(g, r, coarse[0], done);
+            if (fuse_r_old) {
+                launch_sl_down_fused(g, fuse_r_old, r, coarse[0], done);
+                HGTRY(stage_check(d_spart3, sl_ns * sl_nt, (long long)sl_ns * sl_nt));
+            } else if (stream_legs()) launch_sl_down(g, r, coarse[0], done);
             else if (has_pen) mg_down0_kernel<T, true><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, DOWN_H, true>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
             else if (scalar_legs) mg_down0_kernel<T, false><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, DOWN_H, false>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
             else mg_down0v_kernel<T><<<tile_grid(), VR_THREADS, sizeof(VRegionSmem<T>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
@@ -814,13 +825,48 @@ struct Solver : SolverBase {
     size_t sl_smem() const { return (size_t)SL_WPB * SL_RING * 128 * sizeof(T); }   // lean kernels: one ring of rows per warp
     void launch_sl_down(const Grid<T>& g, const T* r, const Coarse<T>& c1, const int* done) {
         const int zx = unfused_coarse ? 1 : 0;
+        const SlFuse nf = {nullptr, nullptr, nullptr, nullptr, 0};
         if (sl_n_down_lean)
-            sl_down_kernel<T, false, true><<<sl_grid(sl_n_down_lean), sl_block(), sl_smem(), stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[0], sl_n_down_lean, sl_ns, zx, done);
+            sl_down_kernel<T, false, true><<<sl_grid(sl_n_down_lean), sl_block(), sl_smem(), stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[0], sl_n_down_lean, sl_ns, zx, done, nf);
         if (sl_n_down_gen) {
-            if (has_soft()) sl_down_kernel<T, true, false><<<sl_grid(sl_n_down_gen), sl_block(), 0, stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[1], sl_n_down_gen, sl_ns, zx, done);
-            else sl_down_kernel<T, false, false><<<sl_grid(sl_n_down_gen), sl_block(), 0, stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[1], sl_n_down_gen, sl_ns, zx, done);
+            if (has_soft()) sl_down_kernel<T, true, false><<<sl_grid(sl_n_down_gen), sl_block(), 0, stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[1], sl_n_down_gen, sl_ns, zx, done, nf);
+            else sl_down_kernel<T, false, false><<<sl_grid(sl_n_down_gen), sl_block(), 0, stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[1], sl_n_down_gen, sl_ns, zx, done, nf);
         }
         launches += (sl_n_down_lean > 0) + (sl_n_down_gen > 0) - 1;
+    }
+    // the same leg with the CG update fused in: r_new = r_old - alpha q (to `r_new`), partial sums of r_new.r_new
+    void launch_sl_down_fused(const Grid<T>& g, const T* r_old, T* r_new, const Coarse<T>& c1, const int* done) {
+        const SlFuse fu = {d_q, r_new, d_state, d_spart3, sl_nt};
+        if (sl_n_down_lean)
+            sl_down_kernel<T, false, true, true><<<sl_grid(sl_n_down_lean), sl_block(), 2 * sl_smem(), stream>>>(g, d_code, r_old, c1, d_sl_tasks + sl_off[0], sl_n_down_lean, sl_ns, 0, done, fu);
+        if (sl_n_down_gen)
+            sl_down_kernel<T, false, false, true><<<sl_grid(sl_n_down_gen), sl_block(), 0, stream>>>(g, d_code, r_old, c1, d_sl_tasks + sl_off[1], sl_n_down_gen, sl_ns, 0, done, fu);
+        launches += (sl_n_down_lean > 0) + (sl_n_down_gen > 0) - 1;
+    }
+    // p_new = z + beta p_old;  x += alpha p_old;  q = A p_new;  partial sums of p_new.q  -- and the scalar stage for alpha
+    int fused_lap_and_alpha(const T* z, const T* p_old, T* p_new, T* x, int first) {
+        const Grid<T> g = grid();
+        if (sl_n_up_lean)
+            sl_lap_fused_kernel<T, false><<<sl_grid(sl_n_up_lean), sl_block(), 2 * sl_smem(), stream>>>(g, d_code, z, p_old, p_new, x, d_q, d_state, first, d_sl_tasks + sl_off[2], sl_n_up_lean, sl_ns, sl_nt, d_spart2);
+        if (sl_n_up_gen)
+            sl_lap_fused_kernel<T, true><<<sl_grid(sl_n_up_gen), sl_block(), 2 * sl_smem(), stream>>>(g, d_code, z, p_old, p_new, x, d_q, d_state, first, d_sl_tasks + sl_off[3], sl_n_up_gen, sl_ns, sl_nt, d_spart2);
+        launches += (sl_n_up_lean > 0) + (sl_n_up_gen > 0);
+        return stage_alpha(d_spart2, sl_ns * sl_nt, (long long)sl_ns * sl_nt);
+    }
+    // the fused loop serves the single-GPU Laplacian + multigrid path without soft weights / penalty edges
+    bool fused_cg() const { return use_mg() && stream_lap() && world == 1 && !coarse.empty() && generic_nu == 0 && !no_fuse; }
+    int ensure_fused_buffers() {
+        const size_t bytes = (size_t)plane * K * sizeof(T);
+        if (!d_p2) { CU(cudaMalloc(&d_p2, bytes)); CU(cudaMemsetAsync(d_p2, 0, bytes, stream)); }
+        if (!d_r2) { CU(cudaMalloc(&d_r2, bytes)); CU(cudaMemsetAsync(d_r2, 0, bytes, stream)); }
+        if (!d_spart3) {
+            CU(cudaMalloc(&d_spart3, (size_t)sl_ns * sl_nt * K * sizeof(double)));
+            CU(cudaMemsetAsync(d_spart3, 0, (size_t)sl_ns * sl_nt * K * sizeof(double), stream));
+        }
+        CU(cudaFuncSetAttribute(sl_down_kernel<T, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SL_WPB * SL_RING * 128 * sizeof(T))));
+        CU(cudaFuncSetAttribute(sl_lap_fused_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SL_WPB * SL_RING * 128 * sizeof(T))));
+        CU(cudaFuncSetAttribute(sl_lap_fused_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SL_WPB * SL_RING * 128 * sizeof(T))));
+        return HG_OK;
     }
     void launch_sl_up(const Grid<T>& g, const T* r, T* z, const Coarse<T>& c1, int have_coarse, const int* done) {
         if (sl_n_up_lean)
@@ -1237,7 +1283,18 @@ struct Solver : SolverBase {
 
             // inner PCG on A e = r, e0 = 0 (fp32 mode) or continuing from x (fp64 mode)
             if (kRefine) CU(cudaMemsetAsync(d_x, 0, vbytes, stream));
-            if (mg) {
+            const bool fuse = mg && fused_cg();
+            T* pbuf[2] = {d_p, d_p2};
+            T* rbuf[2] = {d_r, d_r2};
+            const int iter0 = host.iter;
+            int jq = 0;                 // iterations of this run enqueued so far
+            if (fuse) {
+                HGTRY(ensure_fused_buffers());
+                pbuf[1] = d_p2; rbuf[1] = d_r2;
+                HGTRY(vcycle(d_z, d_r, done, d_tpart1));
+                HGTRY(stage_beta_rz(1));
+                launches += 1;
+            } else if (mg) {
                 HGTRY(vcycle(d_z, d_r, done, d_tpart1));
                 HGTRY(stage_beta_rz(1));
                 cg_pupdate_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, d_p, d_z, d_tile_active, 1);
@@ -1252,7 +1309,15 @@ struct Solver : SolverBase {
             }
             while (true) {
                 for (int s = 0; s < batch; ++s) {
-                    if (mg) {
+                    if (fuse) {
+                        // iteration j: p_j = z + beta p_{j-1} (and x += alpha_{j-1} p_{j-1}), q = A p_j | alpha_j |
+                        // r_j = r_{j-1} - alpha_j q inside the downward leg | check | rest of the V-cycle | beta
+                        ++jq;
+                        HGTRY(fused_lap_and_alpha(d_z, pbuf[(jq - 1) & 1], pbuf[jq & 1], e, jq == 1));
+                        HGTRY(vcycle(d_z, rbuf[jq & 1], done, d_tpart1, rbuf[(jq - 1) & 1]));
+                        HGTRY(stage_beta_rz(0));
+                        launches += 3;
+                    } else if (mg) {
                         HGTRY(exchange(d_p, 1));
                         HGTRY(lap_and_alpha(d_p, d_q, done));
                         launches -= 2;
@@ -1278,6 +1343,11 @@ struct Solver : SolverBase {
                 CU(cudaMemcpyAsync(&host, d_state, sizeof host, cudaMemcpyDeviceToHost, stream));
                 CU(cudaStreamSynchronize(stream));
                 if (host.done) break;
+            }
+            if (fuse && host.iter > iter0 && host.done != 2) {
+                // the update of the last executed iteration J is still owed: x += alpha_J p_J (p_J sits in pbuf[J & 1])
+                cg_xfinal_kernel<T><<<vec_blocks(), 256, 0, stream>>>(d_state, plane, K, e, pbuf[(host.iter - iter0) & 1]);
+                ++launches;
             }
             if (kRefine) {
                 if (mg) axpy_master_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(g, d_xm, d_x, d_tile_active);
