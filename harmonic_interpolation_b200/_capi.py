@@ -12,6 +12,7 @@ FLAG_HARD, FLAG_CUT_DOWN, FLAG_CUT_RIGHT, FLAG_PEN_DOWN, FLAG_PEN_RIGHT, FLAG_SO
 OP_LAPLACIAN, OP_BILAPLACIAN = 0, 1
 PREC_FP32, PREC_FP64 = 0, 1
 PRECOND_JACOBI, PRECOND_MULTIGRID = 0, 1
+EDGES_REFERENCE, EDGES_UNIFORM = 0, 1
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_UNREFERENCED, ERR_EMPTY_ROWS = -1, -2, -3, -4, -5
@@ -26,7 +27,7 @@ class SetupInfo(ctypes.Structure):
 
 
 class Values(ctypes.Structure):
-    _fields_ = [("hard_vals", _dp), ("soft_vals", _dp), ("d_down", _dp), ("d_right", _dp), ("x0", _dp)]
+    _fields_ = [("hard_vals", _dp), ("soft_vals", _dp), ("d_down", _dp), ("d_right", _dp), ("x0", _dp), ("rhs", _dp)]
 
 
 class Stats(ctypes.Structure):
@@ -50,6 +51,7 @@ SYMBOLS = {
     "hg_set_soft_weights": (ctypes.c_int, [_H, _dp, ctypes.c_double]),
     "hg_set_grad_weight": (ctypes.c_int, [_H, ctypes.c_double]),
     "hg_set_preconditioner": (ctypes.c_int, [_H, ctypes.c_int]),
+    "hg_set_edge_weights": (ctypes.c_int, [_H, ctypes.c_int]),
     "hg_setup": (ctypes.c_int, [_H, ctypes.POINTER(SetupInfo)]),
     "hg_apply": (ctypes.c_int, [_H, _dp, _dp]),
     "hg_solve": (ctypes.c_int, [_H, ctypes.POINTER(Values), _dp, ctypes.c_double, ctypes.c_int, ctypes.POINTER(Stats)]),

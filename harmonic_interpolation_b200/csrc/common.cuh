@@ -25,6 +25,7 @@ struct Grid {
     const T* soft;         // per-pixel soft weights or nullptr (then soft_scalar where HG_FLAG_SOFT)
     T soft_scalar;
     T w_g;                 // weight of HG_FLAG_PEN_* edges
+    int uniform;           // 1: every edge weighs 1/4 (poisson.py's G.T*G / 4); 0: 1/8 along the grid border (recovery.py:263-299)
 };
 
 template <typename T> struct V4 { T v[4]; };
@@ -97,7 +98,7 @@ template <typename T>
 __device__ __forceinline__ T w_down(const Grid<T>& g, int i, int j, unsigned f) {
     T w = T(0);
     if (i + 1 < g.rows) {
-        if (!(f & HG_FLAG_CUT_DOWN)) w = (g.cols > 1 && (j == 0 || j == g.cols - 1)) ? T(0.125) : T(0.25);
+        if (!(f & HG_FLAG_CUT_DOWN)) w = (!g.uniform && g.cols > 1 && (j == 0 || j == g.cols - 1)) ? T(0.125) : T(0.25);
         if (f & HG_FLAG_PEN_DOWN) w += g.w_g;
     }
     return w;
@@ -107,7 +108,7 @@ template <typename T>
 __device__ __forceinline__ T w_right(const Grid<T>& g, int i, int j, unsigned f) {
     T w = T(0);
     if (j + 1 < g.cols) {
-        if (!(f & HG_FLAG_CUT_RIGHT)) w = (g.rows > 1 && (i == 0 || i == g.rows - 1)) ? T(0.125) : T(0.25);
+        if (!(f & HG_FLAG_CUT_RIGHT)) w = (!g.uniform && g.rows > 1 && (i == 0 || i == g.rows - 1)) ? T(0.125) : T(0.25);
         if (f & HG_FLAG_PEN_RIGHT) w += g.w_g;
     }
     return w;

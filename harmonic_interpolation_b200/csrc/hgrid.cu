@@ -110,6 +110,7 @@ struct SolverBase {
     virtual int set_soft(const double* w, double scalar) = 0;
     virtual int set_grad_weight(double w) = 0;
     virtual int set_precond(int p) = 0;
+    virtual int set_edges(int mode) = 0;
     virtual int setup(hg_setup_info* info) = 0;
     virtual int apply(const double* x, double* y) = 0;
     virtual int upload(const hg_values* v, hg_stats* st) = 0;
@@ -141,7 +142,8 @@ struct Solver : SolverBase {
     T* d_soft = nullptr;
     T* d_dinv = nullptr;
     T *d_x = nullptr, *d_b = nullptr, *d_r = nullptr, *d_p = nullptr, *d_q = nullptr;
-    double* d_stage[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // staged host arrays
+    double* d_stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // staged host arrays
+    int edge_uniform = 0;
     double* d_out = nullptr;
     double *d_part0 = nullptr, *d_part1 = nullptr;
     int part_cap = 0;
@@ -234,6 +236,7 @@ struct Solver : SolverBase {
         Grid<T> g;
         g.rows = rows; g.cols = cols; g.pitch = pitch; g.plane = plane; g.K = K;
         g.flags = d_flags; g.soft = d_soft; g.soft_scalar = (T)soft_scalar; g.w_g = (T)w_g;
+        g.uniform = edge_uniform;
         return g;
     }
 
@@ -302,6 +305,13 @@ struct Solver : SolverBase {
         return HG_OK;
     }
 
+    int set_edges(int mode) override {
+        if (mode != HG_EDGES_REFERENCE && mode != HG_EDGES_UNIFORM) return fail(HG_ERR_INVALID, "unknown edge-weight mode");
+        if (mode == HG_EDGES_UNIFORM && op != HG_OP_LAPLACIAN) return fail(HG_ERR_INVALID, "uniform edge weights apply to the Laplacian operator only");
+        edge_uniform = mode;
+        is_setup = false;
+        return HG_OK;
+    }
     int set_precond(int p) override {
         if (p != HG_PRECOND_JACOBI && p != HG_PRECOND_MULTIGRID) return fail(HG_ERR_INVALID, "unknown preconditioner");
         precond = p;
@@ -393,7 +403,7 @@ struct Solver : SolverBase {
         cudaMemsetAsync(f, 0, (size_t)n * n, stream);
         Grid<T> g;
         g.rows = g.cols = g.pitch = n; g.plane = (long long)n * n; g.K = 1;
-        g.flags = f; g.soft = nullptr; g.soft_scalar = T(0); g.w_g = T(0);
+        g.flags = f; g.soft = nullptr; g.soft_scalar = T(0); g.w_g = T(0); g.uniform = 0;
         std::vector<Coarse<T>> lv;
         cudaError_t err = cudaSuccess;
         for (int l = 1; l <= REF_LEVELS; ++l) {
@@ -1067,13 +1077,13 @@ struct Solver : SolverBase {
         memset(&z, 0, sizeof z);
         if (!v) v = &z;
         CU(cudaEventRecord(ev0, stream));
-        const double* host[5] = {v->hard_vals, v->soft_vals, v->d_down, v->d_right, v->x0};
-        b_is_zero = !v->soft_vals && !v->d_down && !v->d_right;
-        for (int s = 0; s < 5; ++s) HGTRY(stage(s, host[s]));
+        const double* host[6] = {v->hard_vals, v->soft_vals, v->d_down, v->d_right, v->x0, v->rhs};
+        b_is_zero = !v->soft_vals && !v->d_down && !v->d_right && !v->rhs;
+        for (int s = 0; s < 6; ++s) HGTRY(stage(s, host[s]));
         dim3 pg((pitch + 255) / 256, rows);
         build_problem_kernel<T, double><<<pg, 256, 0, stream>>>(grid(), host[0] ? d_stage[0] : nullptr, host[1] ? d_stage[1] : nullptr,
                                                                host[2] ? d_stage[2] : nullptr, host[3] ? d_stage[3] : nullptr,
-                                                               host[4] ? d_stage[4] : nullptr, d_xm, d_bm);
+                                                               host[4] ? d_stage[4] : nullptr, host[5] ? d_stage[5] : nullptr, d_xm, d_bm);
         CU(cudaEventRecord(ev1, stream));
         CU(cudaStreamSynchronize(stream));
         CU(cudaGetLastError());
@@ -1540,6 +1550,7 @@ int hg_set_flags(hg_handle h, const uint8_t* flags) { CHECK_H(h); return h->impl
 int hg_set_soft_weights(hg_handle h, const double* w, double scalar_w) { CHECK_H(h); return h->impl->set_soft(w, scalar_w); }
 int hg_set_grad_weight(hg_handle h, double w_g) { CHECK_H(h); return h->impl->set_grad_weight(w_g); }
 int hg_set_preconditioner(hg_handle h, int p) { CHECK_H(h); return h->impl->set_precond(p); }
+int hg_set_edge_weights(hg_handle h, int mode) { CHECK_H(h); return h->impl->set_edges(mode); }
 int hg_setup(hg_handle h, hg_setup_info* info) { CHECK_H(h); return h->impl->setup(info); }
 int hg_apply(hg_handle h, const double* x, double* y) { CHECK_H(h); return h->impl->apply(x, y); }
 int hg_upload_values(hg_handle h, const hg_values* v, hg_stats* st) { CHECK_H(h); return h->impl->upload(v, st); }

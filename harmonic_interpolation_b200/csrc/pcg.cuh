@@ -299,7 +299,7 @@ __global__ void reset_guess_kernel(Grid<T> g, double* __restrict__ x) {
 template <typename T, typename TO>
 __global__ void build_problem_kernel(Grid<T> g, const double* __restrict__ hard_vals, const double* __restrict__ soft_vals,
                                      const double* __restrict__ d_down, const double* __restrict__ d_right,
-                                     const double* __restrict__ x0, TO* __restrict__ x, TO* __restrict__ b) {
+                                     const double* __restrict__ x0, const double* __restrict__ rhs, TO* __restrict__ x, TO* __restrict__ b) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
     if (j >= g.pitch) return;
@@ -327,7 +327,7 @@ __global__ void build_problem_kernel(Grid<T> g, const double* __restrict__ hard_
     const bool pu = d_down && i > 0 && (fu & HG_FLAG_PEN_DOWN);
     const bool pl = d_right && j > 0 && (fl & HG_FLAG_PEN_RIGHT);
     for (int k = 0; k < K; ++k) {
-        double v = 0.0;
+        double v = rhs ? rhs[h + k] : 0.0;
         if (sw != 0.0 && soft_vals) v += sw * soft_vals[h + k];
         if (pd) v -= wg * d_down[h + k];
         if (pr) v -= wg * d_right[h + k];

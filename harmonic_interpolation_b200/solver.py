@@ -53,7 +53,7 @@ def encode_flags(rows, cols, hard=None, soft=None, cut_down=None, cut_right=None
 
 
 class GridSolver:
-    def __init__(self, rows, cols, channels=1, bilaplacian=False, precision=None, preconditioner=None):
+    def __init__(self, rows, cols, channels=1, bilaplacian=False, precision=None, preconditioner=None, uniform_edges=False):
         self.rows, self.cols, self.K = int(rows), int(cols), int(channels)
         self.bilaplacian = bool(bilaplacian)
         self.precision = precision or default_precision()
@@ -69,6 +69,9 @@ class GridSolver:
             # multigrid where it exists (the Laplacian); the library uses Jacobi for the bilaplacian
             preconditioner = os.environ.get("HGRID_PRECOND", "multigrid")
         C.check(self._lib.hg_set_preconditioner(self._h, {"jacobi": C.PRECOND_JACOBI, "multigrid": C.PRECOND_MULTIGRID}[preconditioner]))
+        if uniform_edges:
+            # every edge weighs 1/4: the operator is G.T*G / 4 of poisson.py (hg_set_edge_weights)
+            C.check(self._lib.hg_set_edge_weights(self._h, C.EDGES_UNIFORM))
         self.flags = None
         self.info = None
         self.last_stats = None
@@ -116,11 +119,11 @@ class GridSolver:
         return y
 
     def solve(self, hard_vals=None, soft_vals=None, d_down=None, d_right=None, x0=None, rtol=None, maxiter=None,
-              allow_unconverged=False):
+              allow_unconverged=False, rhs=None):
         """Returns float64 (rows, cols, K).  Raises ArithmeticError if the iteration breaks down
         (singular / under-constrained system; cvxopt raises ArithmeticError there too) or does
         not converge (the reference asserts `0 == info`, recovery.py:972)."""
-        keep = [self._vals(a) for a in (hard_vals, soft_vals, d_down, d_right, x0)]
+        keep = [self._vals(a) for a in (hard_vals, soft_vals, d_down, d_right, x0, rhs)]
         vals = C.Values(*[C.dptr(a) for a in keep])
         out = np.empty((self.rows, self.cols, self.K), np.float64)
         stats = C.Stats()
@@ -166,8 +169,8 @@ class GridSolver:
         return out
 
     # ---- three-step form used by bench.py ---------------------------------------------------
-    def upload(self, hard_vals=None, soft_vals=None, d_down=None, d_right=None, x0=None):
-        keep = [self._vals(a) for a in (hard_vals, soft_vals, d_down, d_right, x0)]
+    def upload(self, hard_vals=None, soft_vals=None, d_down=None, d_right=None, x0=None, rhs=None):
+        keep = [self._vals(a) for a in (hard_vals, soft_vals, d_down, d_right, x0, rhs)]
         vals = C.Values(*[C.dptr(a) for a in keep])
         stats = C.Stats()
         C.check(self._lib.hg_upload_values(self._h, ctypes.byref(vals), ctypes.byref(stats)))

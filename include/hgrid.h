@@ -78,6 +78,8 @@ typedef struct {
     const double* d_down;    /* read where HG_FLAG_PEN_DOWN  (recovery.py:552)              */
     const double* d_right;   /* read where HG_FLAG_PEN_RIGHT (recovery.py:557)              */
     const double* x0;        /* optional initial guess on the free pixels                   */
+    const double* rhs;       /* optional explicit right-hand side, added at the free pixels
+                                (G.T * target_gradients of poisson.py:73)                    */
 } hg_values;
 
 typedef struct {
@@ -112,6 +114,11 @@ int hg_set_soft_weights(hg_handle h, const double* weights, double scalar_w);
 /* weight of the dx/dy constraints, w_gradients (recovery.py:875-884, 926-927) */
 int hg_set_grad_weight(hg_handle h, double w_g);
 int hg_set_preconditioner(hg_handle h, int precond);
+/* Edge weights of the Laplacian: HG_EDGES_REFERENCE = gen_symmetric_grid_laplacian2 (1/4, and 1/8 along the
+ * first / last row and column, recovery.py:263-299); HG_EDGES_UNIFORM = 1/4 on every edge, i.e. one quarter of
+ * the graph Laplacian G.T*G of poisson.py:55-56 (gradient_operator, poisson.py:204-251). */
+enum { HG_EDGES_REFERENCE = 0, HG_EDGES_UNIFORM = 1 };
+int hg_set_edge_weights(hg_handle h, int mode);
 /* Validates the domain (recovery.py:484-495) and builds the device-resident operator
  * and preconditioner.  Replaces the factorisation cvxopt.umfpack.numeric
  * (recovery.py:1304); call once, then hg_solve any number of times. */

@@ -553,3 +553,54 @@ def fill_rgba8(rgba):
     mask = (255 * arr[:, :, 3]).round(0).astype(int) == 255
     res = fill_alpha_harmonic(arr[:, :, :3], mask)
     return np.asarray((res * 255).round(0).clip(0, 255), dtype=np.uint8)
+
+
+# --------------------------------------------------------------------------------------
+# poisson.py: gradient-domain integration
+# --------------------------------------------------------------------------------------
+def gradient_operator(rows, cols, mask=None):
+    """poisson.py:204-251, vectorised: G (2 N x N); row (i*cols + j)*2 + k holds the forward difference of
+    pixel (i,j) along axis k (0: i, 1: j); edges across a mask border are left out."""
+    idx = np.arange(rows * cols).reshape(rows, cols)
+    down = np.ones((rows, cols), bool); down[-1, :] = False
+    right = np.ones((rows, cols), bool); right[:, -1] = False
+    if mask is not None:
+        mask = np.asarray(mask, bool)
+        down[:-1] &= mask[:-1] == mask[1:]
+        right[:, :-1] &= mask[:, :-1] == mask[:, 1:]
+    I, J, V = [], [], []
+    p = idx[down]
+    I += [2 * p, 2 * p]; J += [p, p + cols]; V += [-np.ones(len(p)), np.ones(len(p))]
+    p = idx[right]
+    I += [2 * p + 1, 2 * p + 1]; J += [p, p + 1]; V += [-np.ones(len(p)), np.ones(len(p))]
+    return sp.coo_matrix((np.concatenate(V), (np.concatenate(I), np.concatenate(J))), shape=(2 * rows * cols, rows * cols)).tocsr()
+
+
+def solve_poisson_simple(target_gradients, linear_constraints, linear_constraints_weight, mask=None, mask_value=None):
+    """poisson.py:6-99 (Laplacian form): system = G.T G (+ Dirichlet rows for masked pixels, poisson.py:76-82)
+    + w A.T A, rhs = G.T u + w A.T b (poisson.py:85-89, 329-366); sparse direct solve."""
+    u = np.asarray(target_gradients, float)
+    rows, cols, _, K = u.shape
+    N = rows * cols
+    G = gradient_operator(rows, cols, mask)
+    system = (G.T @ G).tocsr()
+    rhs = G.T @ u.reshape(N * 2, K)
+    if mask is not None and mask_value is not None:
+        c = np.flatnonzero(~np.asarray(mask, bool).ravel())
+        vals = np.tile(np.asarray(mask_value, float), (len(c), 1))
+        rhs = rhs - system[:, c] @ vals            # symmetric elimination (poisson.py:253-327)
+        keep = np.ones(N); keep[c] = 0.0
+        D = sp.diags(keep)
+        system = (D @ system @ D + sp.diags(1.0 - keep)).tocsr()
+        rhs[c] = vals
+    I, J, V = [], [], []
+    b = np.zeros((len(linear_constraints), K))
+    for n, (coeffs, value) in enumerate(linear_constraints):
+        for i, j, cf in coeffs:
+            I.append(n); J.append(i * cols + j); V.append(cf)
+        b[n] = value
+    A = sp.coo_matrix((V, (I, J)), shape=(len(linear_constraints), N)).tocsr()
+    system = system + linear_constraints_weight * (A.T @ A)
+    rhs = rhs + linear_constraints_weight * (A.T @ b)
+    x = spla.splu(system.tocsc()).solve(rhs)
+    return x.reshape(rows, cols, K)

@@ -90,7 +90,7 @@ _loaded = {}
 
 
 def load_reference():
-    """Returns the reference's modules as a dict: recovery, fill_alpha_harmonic, highlighting."""
+    """Returns the reference's modules as a dict: recovery, fill_alpha_harmonic, highlighting, poisson."""
     if _loaded:
         return _loaded
     if not have_reference():
@@ -102,7 +102,7 @@ def load_reference():
     # names from REFERENCE_DIR, then restore sys.path and sys.modules so that the
     # product's same-named drop-in modules are never shadowed.
     saved_path = list(sys.path)
-    names = ["tictoc", "recovery", "fill_alpha_harmonic", "highlighting"]
+    names = ["tictoc", "recovery", "fill_alpha_harmonic", "highlighting", "poisson"]
     saved_mods = {n: sys.modules.pop(n, None) for n in names}
     sys.path.insert(0, REFERENCE_DIR)
     try:

@@ -1,0 +1,18 @@
+"""The stored inputs of tests/golden/reference_poisson.npz (written by oracle/make_golden_poisson.py from the
+unmodified reference) as keyword arguments of solve_poisson_simple."""
+import os
+
+import numpy as np
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_poisson.npz")
+NAMES = ("plain", "rgb", "masked", "island")
+
+
+def load(name):
+    z = np.load(GOLD)
+    lc = [([(int(i), int(j), float(c))], v) for (i, j), c, v in zip(z[name + "_ij"], z[name + "_coeff"], z[name + "_vals"])]
+    kw = dict(target_gradients=z[name + "_u"], linear_constraints=lc, linear_constraints_weight=float(z[name + "_w"]))
+    if name + "_mask" in z.files:
+        kw["mask"] = z[name + "_mask"]
+        kw["mask_value"] = z[name + "_mask_value"]
+    return kw, z[name + "_out"]

@@ -98,3 +98,13 @@ def test_reflected_domain_asserts():
     with pytest.raises(AssertionError):
         go.reflected_laplacian_matrix(2, 2)
     go.reflected_laplacian_matrix(3, 3)
+
+
+@pytest.mark.parametrize("name", ["plain", "rgb", "masked", "island"])
+def test_poisson_oracle_matches_reference_golden(name):
+    """oracle restatement of poisson.solve_poisson_simple (poisson.py:6-99) against outputs of the unmodified reference"""
+    import poisson_cases as pc
+    kw, want = pc.load(name)
+    got = go.solve_poisson_simple(kw["target_gradients"], kw["linear_constraints"], kw["linear_constraints_weight"],
+                                  kw.get("mask"), kw.get("mask_value"))
+    assert np.abs(got - want).max() <= 1e-9 * max(1.0, np.abs(want).max())
