@@ -120,7 +120,8 @@ def test_compat_modules_export_reference_names():
             "from recovery import solve_grid_linear, solve_grid_linear_simple, solve_grid_linear_simple3, "
             "solve_grid_linear_simple3_solver, smooth_bumps, smooth_bumps2, cut_edges_from_mask, "
             "zero_dx_dy_constraints_from_cut_edges, convert_grid_normal_constraints_to_dx_and_dy_constraints, normalize_to_char_img;"
-            "from highlighting import grow, shrink; from tictoc import tic, toc; print('ok')")
+            "from highlighting import grow, shrink; from tictoc import tic, toc;"
+            "from poisson import solve_poisson_simple; print('ok')")
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, os.path.join(ROOT, "harmonic_interpolation_b200", "compat")]))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/tmp")
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr
