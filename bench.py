@@ -73,9 +73,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples that arrived during [t0, t1] (the timed region); if nvidia-smi was too slow to
+        deliver one inside the window, the samples nearest to it are used and the fact is noted."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -83,21 +85,34 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        rows = []
+        for t, s in self.samples:
             f = [x.strip() for x in s.split(",")]
             if len(f) < 6:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                rows.append((t, float(f[0]), float(f[1]), f[2:6]))
             except ValueError:
                 continue
-            for name, v in zip(names, f[2:6]):
+        note = None
+        sel = rows
+        if t0 is not None and rows:
+            sel = [r for r in rows if t0 - 0.15 <= r[0] <= t1 + 0.15]
+            if not sel:
+                mid = 0.5 * (t0 + t1)
+                sel = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
+                note = "no sample inside the timed window (%.2f s); nearest samples used" % (t1 - t0)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for r in sel:
+            for name, v in zip(names, r[3]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": float(np.median([r[1] for r in sel])) if sel else None, "sm_max_mhz": max(r[2] for r in sel) if sel else None,
+               "reasons": sorted(reasons), "samples": len(sel)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def cpu_fill(n):
@@ -189,12 +204,13 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: device-resident solve; every step restarts from the zero guess ----------------
+    sampler = ClockSampler(local)
+    sampler.start()                      # nvidia-smi needs a second or so to deliver its first line: start before the warm-up
     for _ in range(args.warmup):
         s.reset_guess()
         st = s.solve_device(args.rtol, 500)
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
+    t_win0 = time.perf_counter()
     dev_ms, launches, iters, relres = [], 0, 0, 0.0
     for _ in range(args.steps):
         s.reset_guess()
@@ -204,7 +220,7 @@ def main():
         iters = st["iterations"]
         relres = st["relres"]
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_win0, time.perf_counter())
     t_dev = torch.tensor([sum(dev_ms)], dtype=torch.float64, device="cuda")
     tot_unknowns = torch.tensor([unknowns], dtype=torch.float64, device="cuda")
     if world > 1:

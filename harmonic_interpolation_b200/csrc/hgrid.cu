@@ -173,6 +173,9 @@ struct Solver : SolverBase {
     std::vector<Lev25<T>> lev25;
     double* d_dense25 = nullptr;
     int mg25_sweeps = getenv("HGRID_MG25_SWEEPS") ? atoi(getenv("HGRID_MG25_SWEEPS")) : 1;
+    int mg25_agg_levels = getenv("HGRID_MG25_AGG") ? atoi(getenv("HGRID_MG25_AGG")) : 3;   // finest levels that get the aggregate correction
+    double mg25_agg_theta = getenv("HGRID_MG25_THETA") ? atof(getenv("HGRID_MG25_THETA")) : 10.0;   // strong: |a_pq| > theta * interior diagonal
+    int* d_changed = nullptr;
     // tile path (Laplacian + multigrid): activity map and per-tile partial sums
     uint8_t* d_tile_active = nullptr;
     double *d_tpart0 = nullptr, *d_tpart1 = nullptr;
@@ -214,7 +217,7 @@ struct Solver : SolverBase {
         cudaFree(d_tile_active); cudaFree(d_tpart0); cudaFree(d_tpart1);
         cudaFree(d_down_active); cudaFree(d_code); cudaFree(d_lpart);
         cudaFree(d_sl_up); cudaFree(d_sl_down); cudaFree(d_spart); cudaFree(d_spart2); cudaFree(d_sl_tasks);
-        cudaFree(d_p2); cudaFree(d_r2); cudaFree(d_spart3);
+        cudaFree(d_p2); cudaFree(d_r2); cudaFree(d_spart3); cudaFree(d_changed);
         if (comm && g_nccl.ok) g_nccl.CommDestroy(comm);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -356,7 +359,7 @@ struct Solver : SolverBase {
         cudaFree(d_dense); cudaFree(d_gdense);
         d_dense = d_gdense = nullptr;
         for (size_t l = 0; l < lev25.size(); ++l) {
-            cudaFree(lev25[l].coef);
+            cudaFree(lev25[l].coef); cudaFree(lev25[l].label); cudaFree(lev25[l].aggD); cudaFree(lev25[l].aggS);
             if (l > 0) { cudaFree(lev25[l].x); cudaFree(lev25[l].b); }
         }
         lev25.clear();
@@ -546,6 +549,7 @@ struct Solver : SolverBase {
             L.plane = (long long)L.rows * L.pitch;
             L.K = K;
             L.coef = L.x = L.b = nullptr;
+            L.label = nullptr; L.aggD = nullptr; L.aggS = nullptr;
             CU(cudaMalloc(&L.coef, (size_t)L.plane * 25 * sizeof(T)));
             if (level > 0) {
                 CU(cudaMalloc(&L.x, (size_t)L.plane * K * sizeof(T)));
@@ -556,6 +560,9 @@ struct Solver : SolverBase {
             dim3 cg((L.pitch + 127) / 128, L.rows);
             if (level == 0) assemble25_kernel<T><<<cg, 128, 0, stream>>>(grid(), L);
             else galerkin25_kernel<T><<<cg, 128, 0, stream>>>(Acc25<T>{lev25.back()}, L);
+            // interior diagonal of the unconstrained operator on this level: 20/16, a quarter per level (P^T A P of a
+            // 4th-order operator with bilinear P) -- the scale a coupling must exceed to count as stiff
+            if (level < mg25_agg_levels && (long long)r * c > 256) HGTRY(build_aggregates(L, 1.25 * pow(0.25, level)));
             lev25.push_back(L);
             if ((long long)r * c <= 256) break;
             r = (r + 1) / 2; c = (c + 1) / 2;
@@ -568,6 +575,36 @@ struct Solver : SolverBase {
         gauss_jordan_kernel<<<1, 1024, 2 * n * sizeof(double), stream>>>(d_dense25, n);
         CU(cudaGetLastError());
         return HG_OK;
+    }
+    // clusters of stiffly coupled pixels of a level (mg25.cuh); leaves L.label == nullptr if there are none
+    int build_aggregates(Lev25<T>& L, double ref_diag) {
+        if (!d_changed) CU(cudaMalloc(&d_changed, sizeof(int)));
+        CU(cudaMalloc(&L.label, (size_t)L.plane * sizeof(int)));
+        CU(cudaMalloc(&L.aggD, (size_t)L.plane * sizeof(double)));
+        const T thr = (T)(mg25_agg_theta * ref_diag);
+        dim3 pg((L.pitch + 255) / 256, L.rows);
+        agg_label_init_kernel<T><<<pg, 256, 0, stream>>>(L, thr);
+        int rounds = 0, changed = 1;
+        while (changed && rounds < 4096) {
+            CU(cudaMemsetAsync(d_changed, 0, sizeof(int), stream));
+            for (int s = 0; s < 4; ++s) agg_label_step_kernel<T><<<pg, 256, 0, stream>>>(L, thr, d_changed);
+            CU(cudaMemcpyAsync(&changed, d_changed, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CU(cudaStreamSynchronize(stream));
+            rounds += 4;
+        }
+        agg_diag_kernel<T><<<pg, 256, 0, stream>>>(L);
+        CU(cudaMalloc(&L.aggS, (size_t)L.plane * K * sizeof(double)));
+        CU(cudaMemsetAsync(L.aggS, 0, (size_t)L.plane * K * sizeof(double), stream));
+        CU(cudaGetLastError());
+        return HG_OK;
+    }
+    void agg25(const Lev25<T>& L, const int* done) {
+        if (!L.label) return;
+        dim3 pg((L.cols + 255) / 256, L.rows);
+        agg_zero_kernel<T><<<pg, 256, 0, stream>>>(L, done);
+        agg_resid_kernel<T><<<pg, 256, 0, stream>>>(L, done);
+        agg_apply_kernel<T><<<pg, 256, 0, stream>>>(L, done);
+        launches += 3;
     }
     void gs25(const Lev25<T>& L, bool forward, const int* done) {
         dim3 gg(((L.cols + 2) / 3 + 127) / 128, (L.rows + 2) / 3);
@@ -582,6 +619,7 @@ struct Solver : SolverBase {
         const int n = (int)lev25.size();
         for (int l = 0; l + 1 < n; ++l) {
             gs25(lev25[l], true, done);
+            agg25(lev25[l], done);
             const Lev25<T>& Lc = lev25[l + 1];
             resid_restrict25_kernel<T><<<dim3((Lc.pitch + 127) / 128, Lc.rows), 128, 0, stream>>>(lev25[l], Lc, done);
         }
@@ -589,6 +627,7 @@ struct Solver : SolverBase {
         coarsest_dense25_kernel<T><<<K, 256, Lb.rows * Lb.cols * sizeof(double), stream>>>(Lb, d_dense25, done);
         for (int l = n - 2; l >= 0; --l) {
             prolong_add25_kernel<T><<<dim3((lev25[l].cols + 255) / 256, lev25[l].rows), 256, 0, stream>>>(lev25[l], lev25[l + 1], done);
+            agg25(lev25[l], done);
             gs25(lev25[l], false, done);
         }
         launches += 2 * (n - 1) + 2;

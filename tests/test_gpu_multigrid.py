@@ -214,3 +214,34 @@ def test_bilaplacian_mg_iterations_do_not_grow_with_the_grid():
         s.close()
     assert its[2] <= 1.5 * its[0] + 5, its
     assert its[2] < 120, its
+
+
+def test_bilaplacian_stiff_gradient_constraints_aggregate_correction(monkeypatch):
+    """solve_grid_linear's default w_lsq = 1e5 couples pixel pairs 10^5 times more strongly than the stencil
+    does.  The aggregate correction of mg25.cuh (one Jacobi step on the clusters' indicator vectors after the
+    Gauss-Seidel sweep) must cut the MG-PCG iteration count several times, and the answer must still be the
+    direct solver's (cond ~ 1e11, so two float64 solvers already differ by ~cond * eps: parity <= 2e-5 of the range)."""
+    n = 128
+    rng = np.random.default_rng(0)
+    p = go.GridProblem(n, n, 1, True)
+    p.hard = np.zeros((n, n), bool); p.hard[0, 0] = True
+    p.hard_vals = np.zeros((n, n, 1))
+    pen = rng.random((n, n)) < 0.02
+    p.pen_down = pen.copy(); p.pen_down[-1, :] = False
+    p.pen_right = pen.copy(); p.pen_right[:, -1] = False
+    ii, jj = np.indices((n, n))
+    z = 10.0 * np.sin(2 * np.pi * ii / n) * np.cos(2 * np.pi * jj / n)
+    p.d_down = np.zeros((n, n, 1)); p.d_right = np.zeros((n, n, 1))
+    p.d_down[:-1, :, 0] = z[1:] - z[:-1]; p.d_right[:, :-1, 0] = z[:, 1:] - z[:, :-1]
+    p.w_g = 1e5
+    ref = go.solve_problem(p)
+    its = {}
+    for agg in ("3", "0"):
+        monkeypatch.setenv("HGRID_MG25_AGG", agg)
+        s = bilap_solver(p, "fp64", "multigrid")
+        out = s.solve(p.hard_vals, None, p.d_down, p.d_right, rtol=1e-11, maxiter=50000, allow_unconverged=True)
+        its[agg] = s.last_stats["iterations"]
+        assert s.last_stats["relres"] < 1e-9
+        assert rel_err(out, ref) < 2e-5
+        s.close()
+    assert its["3"] * 2 < its["0"], its
