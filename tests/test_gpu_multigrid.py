@@ -245,3 +245,50 @@ def test_bilaplacian_stiff_gradient_constraints_aggregate_correction(monkeypatch
         assert rel_err(out, ref) < 2e-5
         s.close()
     assert its["3"] * 2 < its["0"], its
+
+
+@pytest.mark.parametrize("K", [1, 4, 5, 7])
+def test_streaming_kernels_any_channel_count(K):
+    """The streaming level-0 kernels map warps to (chunk, channel) pairs and the coarse legs take channel groups
+    of four: any K must give the oracle's answer (fill workload: hard pixels only, several chunks in each direction)."""
+    rows, cols = 200, 300
+    rng = np.random.default_rng(K)
+    hard = np.kron(rng.random((rows // 20, cols // 20)) < 0.5, np.ones((20, 20), bool))
+    hard[0, 0] = True
+    vals = rng.random((rows, cols, K))
+    p = go.GridProblem(rows, cols, K, False)
+    p.hard, p.hard_vals = hard, vals
+    ref = go.solve_problem(p)
+    for prec, tol in (("fp64", 1e-9), ("fp32", 1e-5)):
+        s = S.GridSolver(rows, cols, K, False, prec, "multigrid")
+        s.set_pattern(S.encode_flags(rows, cols, hard=hard))
+        out = s.solve(hard_vals=vals)
+        assert rel_err(out, ref) < tol
+        s.close()
+
+
+def test_fused_cg_loop_matches_the_separate_kernels(monkeypatch):
+    """HGRID_FUSE=1 (p-update + x-update inside the stencil kernel, r-update inside the downward leg) is the same
+    iteration: same iteration count, same answer to rounding."""
+    rows, cols, K = 333, 260, 3
+    rng = np.random.default_rng(2)
+    hard = np.kron(rng.random((rows // 16 + 1, cols // 16 + 1)) < 0.5, np.ones((16, 16), bool))[:rows, :cols]
+    hard[0, 0] = True
+    vals = rng.random((rows, cols, K))
+    res = {}
+    for fuse in (False, True):
+        if fuse:
+            monkeypatch.setenv("HGRID_FUSE", "1")
+        else:
+            monkeypatch.delenv("HGRID_FUSE", raising=False)
+        for prec in ("fp32", "fp64"):
+            s = S.GridSolver(rows, cols, K, False, prec, "multigrid")
+            s.set_pattern(S.encode_flags(rows, cols, hard=hard))
+            out = s.solve(hard_vals=vals, rtol=1e-8)
+            res[(fuse, prec)] = (out, s.last_stats["iterations"])
+            s.close()
+    for prec, tol in (("fp32", 1e-6), ("fp64", 1e-10)):
+        a, ia = res[(False, prec)]
+        b, ib = res[(True, prec)]
+        assert abs(ia - ib) <= 1, (prec, ia, ib)
+        assert np.abs(a - b).max() < tol
