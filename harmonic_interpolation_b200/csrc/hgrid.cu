@@ -191,6 +191,33 @@ struct Solver : SolverBase {
     // per-chunk partial sums of r.r
     T *d_p2 = nullptr, *d_r2 = nullptr;
     double* d_spart3 = nullptr;
+    // HGRID_PHASES=1: CUDA-event time of the phases of the MG-PCG loop, printed to stderr after the solve (debug aid)
+    bool phase_timing = getenv("HGRID_PHASES") != nullptr;
+    std::vector<cudaEvent_t> phase_ev;
+    std::vector<int> phase_id;
+    void mark(int id) {
+        if (!phase_timing) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, stream);
+        phase_ev.push_back(e);
+        phase_id.push_back(id);
+    }
+    void report_phases() {
+        if (!phase_timing || phase_ev.empty()) return;
+        static const char* names[] = {"start", "p-exchange + stencil + alpha", "x/r update + check", "V-cycle: fine down", "V-cycle: coarse levels", "V-cycle: fine up", "beta + p update", "outer residual"};
+        double tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (size_t i = 1; i < phase_ev.size(); ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, phase_ev[i - 1], phase_ev[i]);
+            tot[phase_id[i]] += ms;
+        }
+        fprintf(stderr, "[hgrid rank %d] phases (ms):", rank);
+        for (int k = 1; k < 8; ++k) fprintf(stderr, "  %s %.2f |", names[k], tot[k]);
+        fprintf(stderr, "\n");
+        for (auto e : phase_ev) cudaEventDestroy(e);
+        phase_ev.clear(); phase_id.clear();
+    }
     bool no_fuse = getenv("HGRID_FUSE") == nullptr;      // the fused loop is opt-in (HGRID_FUSE=1): it does not pay yet
     int sl_ns = 0, sl_nt = 0;
     int* d_sl_tasks = nullptr;
@@ -825,7 +852,7 @@ struct Solver : SolverBase {
             if (fuse_r_old) {
                 launch_sl_down_fused(g, fuse_r_old, r, coarse[0], done);
                 HGTRY(stage_check(d_spart3, sl_ns * sl_nt, (long long)sl_ns * sl_nt));
-            } else if (stream_legs()) launch_sl_down(g, r, coarse[0], done);
+            } else if (stream_legs()) { launch_sl_down(g, r, coarse[0], done); mark(3); }
             else if (has_pen) mg_down0_kernel<T, true><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, DOWN_H, true>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
             else if (scalar_legs) mg_down0_kernel<T, false><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, DOWN_H, false>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
             else mg_down0v_kernel<T><<<tile_grid(), VR_THREADS, sizeof(VRegionSmem<T>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
@@ -858,7 +885,8 @@ struct Solver : SolverBase {
         Coarse<T> c0;
         memset(&c0, 0, sizeof c0);
         if (nl > 0) c0 = coarse[0];
-        if (stream_legs()) launch_sl_up(g, r, z, c0, nl > 0, done);
+        mark(4);
+        if (stream_legs()) { launch_sl_up(g, r, z, c0, nl > 0, done); mark(5); }
         else if (has_pen) mg_up0_kernel<T, true><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, UP_H, true>), stream>>>(g, d_code, r, z, c0, nl > 0, d_tile_active, part_rz, done);
         else if (scalar_legs) mg_up0_kernel<T, false><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, UP_H, false>), stream>>>(g, d_code, r, z, c0, nl > 0, d_tile_active, part_rz, done);
         else mg_up0v_kernel<T><<<tile_grid(), VR_THREADS, sizeof(VRegionSmem<T>), stream>>>(g, d_code, r, z, c0, nl > 0, d_tile_active, part_rz, done);
@@ -1367,14 +1395,18 @@ struct Solver : SolverBase {
                         HGTRY(stage_beta_rz(0));
                         launches += 3;
                     } else if (mg) {
+                        mark(0);
                         HGTRY(exchange(d_p, 1));
                         HGTRY(lap_and_alpha(d_p, d_q, done));
                         launches -= 2;
+                        mark(1);
                         cg_update_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, e, d_r, d_p, d_q, d_tile_active, d_tpart0);
                         HGTRY(stage_check(tile_part(d_tpart0), n_own_tiles(), nt));
+                        mark(2);
                         HGTRY(vcycle(d_z, d_r, done, d_tpart1));
                         HGTRY(stage_beta_rz(0));
                         cg_pupdate_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, d_p, d_z, d_tile_active, 0);
+                        mark(6);
                         launches += 6;
                     } else {
                         launch_op<0, 1>(d_p, nullptr, d_q, d_part0, done);
@@ -1410,6 +1442,7 @@ struct Solver : SolverBase {
         CU(cudaGetLastError());
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, ev0, ev1));
+        report_phases();
 
         double relres = sqrt(host.outer_ratio), relres_cg = 0.0;
         for (int k = 0; k < K; ++k)
