@@ -452,8 +452,9 @@ struct SlLeanUp : SlLean<T> {
         B::template update<C2, C3, C1, PAR>(r2);               // red pixels of row i - 2 again
         const int io = i - 2;
         if (io >= B::i0 && io < B::i0 + SL_R && B::owner && B::M[C2]) {
-#pragma unroll
-            for (int p = 0; p < 4; ++p) acc += (double)(B::Z[C2].v[p] * r2.v[p]);
+            // the row's four products in T, then fp64 (conversions and fp64 adds are the slow instructions here)
+            const T part = (B::Z[C2].v[0] * r2.v[0] + B::Z[C2].v[1] * r2.v[1]) + (B::Z[C2].v[2] * r2.v[2] + B::Z[C2].v[3] * r2.v[3]);
+            acc += (double)part;
             st4(zk + (io * B::pitch + B::c0), B::Z[C2]);
         }
     }
