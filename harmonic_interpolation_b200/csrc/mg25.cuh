@@ -319,6 +319,45 @@ agg_label_step_kernel(Lev25<T> L, T thr, int* __restrict__ changed) {
         }
     if (best < lab) { L.label[o] = best; *changed = 1; }
 }
+// cluster sizes (into aggD at the roots, as counts), then: clusters larger than `maxc` are dissolved -- near
+// percolation they span the grid, their indicator is no longer a local mode, and thousands of atomic adds
+// onto one root would serialise
+template <typename T>
+__global__ void __launch_bounds__(256)
+agg_count_kernel(Lev25<T> L) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= L.cols) return;
+    const long long o = (long long)i * L.pitch + j;
+    const int lab = L.label[o];
+    if (lab >= 0) atomicAdd(&L.aggD[lab], 1.0);
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+agg_prune_kernel(Lev25<T> L, double maxc, int* __restrict__ scratch, unsigned long long* __restrict__ kept) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= L.cols) return;
+    const long long o = (long long)i * L.pitch + j;
+    const int lab = L.label[o];
+    int out = lab;
+    if (lab >= 0) {
+        const double n = L.aggD[lab];
+        if (n < 2.0 || n > maxc) out = -1;
+        else atomicAdd(kept, 1ull);
+    }
+    scratch[o] = out;        // labels are read by other threads until everybody has looked: write to a copy
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+agg_commit_kernel(Lev25<T> L, const int* __restrict__ scratch) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= L.pitch) return;
+    const long long o = (long long)i * L.pitch + j;
+    L.label[o] = j < L.cols ? scratch[o] : -1;
+    L.aggD[o] = 0.0;
+}
 // aggD[root] = sum over the cluster's pixels p, q of a_pq
 template <typename T>
 __global__ void __launch_bounds__(256)

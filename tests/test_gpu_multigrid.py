@@ -218,8 +218,9 @@ def test_bilaplacian_mg_iterations_do_not_grow_with_the_grid():
 
 def test_bilaplacian_stiff_gradient_constraints_aggregate_correction(monkeypatch):
     """solve_grid_linear's default w_lsq = 1e5 couples pixel pairs 10^5 times more strongly than the stencil
-    does.  The aggregate correction of mg25.cuh (one Jacobi step on the clusters' indicator vectors after the
-    Gauss-Seidel sweep) must cut the MG-PCG iteration count several times, and the answer must still be the
+    does.  The (experimental, opt-in) aggregate correction of mg25.cuh -- one Jacobi step on the clusters'
+    indicator vectors after the Gauss-Seidel sweep -- cuts the MG-PCG iteration count at this size; with and
+    without it the answer must be the
     direct solver's (cond ~ 1e11, so two float64 solvers already differ by ~cond * eps: parity <= 2e-5 of the range)."""
     n = 128
     rng = np.random.default_rng(0)
