@@ -61,6 +61,7 @@ struct Nccl {
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -86,6 +87,7 @@ static int nccl_load() {
     HG_SYM(Send, "ncclSend");
     HG_SYM(Recv, "ncclRecv");
     HG_SYM(Broadcast, "ncclBroadcast");
+    HG_SYM(AllGather, "ncclAllGather");
     HG_SYM(GroupStart, "ncclGroupStart");
     HG_SYM(GroupEnd, "ncclGroupEnd");
     HG_SYM(GetErrorString, "ncclGetErrorString");
@@ -163,6 +165,7 @@ struct Solver : SolverBase {
     int rank = 0, world = 1, ghost_top = 0, ghost_bottom = 0, global_rows = 0;
     std::vector<int> row_starts;             // first owned global row of every rank (+ global_rows at the end)
     std::vector<Coarse<T>> gcoarse;          // replicated global hierarchy from level HG_GATHER_LEVEL down
+    int* d_gl_rows = nullptr;                // [2 q] first row, [2 q + 1] row count of rank q at the gather level
     double* d_gdense = nullptr;
 
     // multigrid hierarchy (levels >= 1; level 0 is the flag-encoded operator)
@@ -220,6 +223,7 @@ struct Solver : SolverBase {
         for (auto e : phase_ev) cudaEventDestroy(e);
         phase_ev.clear(); phase_id.clear();
     }
+    bool exchange_p = getenv("HGRID_EXCHANGE_P") != nullptr;
     bool no_fuse = getenv("HGRID_FUSE") == nullptr;      // the fused loop is opt-in (HGRID_FUSE=1): it does not pay yet
     int sl_ns = 0, sl_nt = 0;
     int* d_sl_tasks = nullptr;
@@ -247,6 +251,7 @@ struct Solver : SolverBase {
         cudaFree(d_down_active); cudaFree(d_code); cudaFree(d_lpart);
         cudaFree(d_sl_up); cudaFree(d_sl_down); cudaFree(d_spart); cudaFree(d_spart2); cudaFree(d_sl_tasks);
         cudaFree(d_p2); cudaFree(d_r2); cudaFree(d_spart3); cudaFree(d_changed);
+        cudaFree(d_gl_rows); cudaFree(d_gsend);
         if (comm && g_nccl.ok) g_nccl.CommDestroy(comm);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -522,22 +527,44 @@ struct Solver : SolverBase {
     int gl_start(int q) const { return row_starts[q] >> HG_GATHER_LEVEL; }
     int gl_end(int q) const { return q == world - 1 ? chain(global_rows, HG_GATHER_LEVEL) : row_starts[q + 1] >> HG_GATHER_LEVEL; }
 
-    // every rank's owned rows of `nplanes` planes of the local gather level -> the global level
+    // every rank's owned rows of `nplanes` planes of the local gather level -> the global level: packed into one
+    // equal-sized block per rank, ONE all-gather, unpacked (a broadcast per plane and rank cost 24 collectives per
+    // V-cycle on 8 GPUs)
+    T *d_gsend = nullptr, *d_grecv = nullptr;
+    size_t gbuf_elems = 0;
     int gather_level(const T* local, long long lplane, T* global, long long gplane, int pitch_, int nplanes) {
         const ncclDataType_t dt = sizeof(T) == 8 ? ncclDouble : ncclFloat;
         const int gtL = ghost_top >> HG_GATHER_LEVEL;
-        NC(g_nccl.GroupStart());
+        int maxrows = 0;
+        for (int q = 0; q < world; ++q) maxrows = std::max(maxrows, gl_end(q) - gl_start(q));
+        const size_t block = (size_t)nplanes * maxrows * pitch_;
+        if (block * (world + 1) > gbuf_elems) {
+            cudaFree(d_gsend);
+            d_gsend = nullptr;
+            gbuf_elems = block * (world + 1);
+            CU(cudaMalloc(&d_gsend, gbuf_elems * sizeof(T)));
+            d_grecv = d_gsend + block;
+        } else {
+            d_grecv = d_gsend + block;
+        }
+        const int myrows = gl_end(rank) - gl_start(rank);
         for (int c = 0; c < nplanes; ++c)
-            for (int q = 0; q < world; ++q) {
-                T* dst = global + (long long)c * gplane + (long long)gl_start(q) * pitch_;
-                const T* src = q == rank ? local + (long long)c * lplane + (long long)gtL * pitch_ : dst;
-                NC(g_nccl.Broadcast(src, dst, (size_t)(gl_end(q) - gl_start(q)) * pitch_, dt, q, comm, stream));
-            }
-        NC(g_nccl.GroupEnd());
+            CU(cudaMemcpyAsync(d_gsend + (size_t)c * maxrows * pitch_, local + (long long)c * lplane + (long long)gtL * pitch_,
+                               (size_t)myrows * pitch_ * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+        NC(g_nccl.AllGather(d_gsend, d_grecv, block, dt, comm, stream));
+        gather_unpack_kernel<T><<<dim3((pitch_ + 255) / 256, maxrows, world * nplanes), 256, 0, stream>>>(
+            d_grecv, global, gplane, pitch_, maxrows, nplanes, d_gl_rows);
         return HG_OK;
     }
 
     int build_global_hierarchy() {
+        {
+            std::vector<int> gl(2 * world);
+            for (int q = 0; q < world; ++q) { gl[2 * q] = gl_start(q); gl[2 * q + 1] = gl_end(q) - gl_start(q); }
+            if (!d_gl_rows) CU(cudaMalloc(&d_gl_rows, 2 * world * sizeof(int)));
+            CU(cudaMemcpyAsync(d_gl_rows, gl.data(), 2 * world * sizeof(int), cudaMemcpyHostToDevice, stream));
+            CU(cudaStreamSynchronize(stream));
+        }
         const Coarse<T>& Ll = coarse.back();      // local level HG_GATHER_LEVEL
         Coarse<T> G;
         HGTRY(alloc_level(G, chain(global_rows, HG_GATHER_LEVEL), Ll.cols));
@@ -1416,7 +1443,9 @@ struct Solver : SolverBase {
                         launches += 3;
                     } else if (mg) {
                         mark(0);
-                        HGTRY(exchange(d_p, 1));
+                        // (no exchange of p: its ghost rows are computed redundantly from z and the old p, and are
+                        // valid next to the owned band just as the ghost rows of z are; HGRID_EXCHANGE_P=1 restores it)
+                        if (exchange_p) HGTRY(exchange(d_p, 1));
                         HGTRY(lap_and_alpha(d_p, d_q, done));
                         launches -= 2;
                         mark(1);

@@ -400,4 +400,16 @@ coarsest_dense_kernel(Coarse<T> L, const double* __restrict__ M, const int* __re
     }
 }
 
+// slab mode: rows of the all-gathered blocks ([rank][plane][maxrows x pitch]) -> the replicated global level
+template <typename T>
+__global__ void gather_unpack_kernel(const T* __restrict__ recv, T* __restrict__ global, long long gplane, int pitch, int maxrows,
+                                     int nplanes, const int* __restrict__ gl_rows) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    const int q = blockIdx.z / nplanes, c = blockIdx.z - q * nplanes;
+    if (j >= pitch || i >= gl_rows[2 * q + 1]) return;
+    global[(long long)c * gplane + (long long)(gl_rows[2 * q] + i) * pitch + j] =
+        recv[((long long)(q * nplanes + c) * maxrows + i) * pitch + j];
+}
+
 }  // namespace hg
