@@ -171,6 +171,12 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # A multi-rank run that stops making progress (rendezvous, NCCL bootstrap, a collective one rank never enters)
+    # must not sit on N GPUs until somebody else's limit kills it: after HGRID_BENCH_WATCHDOG seconds (default 600)
+    # every rank dumps its Python stacks to stderr and exits.
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("HGRID_BENCH_WATCHDOG", 600)), exit=True)
+
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local)
@@ -274,6 +280,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
+        faulthandler.cancel_dump_traceback_later()
         return
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -298,6 +305,7 @@ def main():
                      "bytes_basis": "pixels of the tiles the kernel touches (tiles without a free pixel are skipped)",
                      "full_grid_bytes_per_launch": alg_bytes_full, "full_grid_gbs": alg_bytes_full / (ms_apply * 1e-3) / 1e9},
     }
+    faulthandler.cancel_dump_traceback_later()
     if not args.no_cpu_baseline:
         u, dt = cpu_fill(CPU_SAMPLE_N)
         line["cpu_baseline"] = {"value": u / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
