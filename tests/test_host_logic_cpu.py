@@ -29,3 +29,23 @@ def test_cut_planes_match_cut_edges_from_mask():
     cd2, cr2, n = R._cut_planes(13, 17, edges)
     assert n == len(edges) == int(cd.sum() + cr.sum())
     assert (cd == cd2).all() and (cr == cr2).all()
+
+
+def test_poisson_gradient_rhs_matches_the_gradient_operator():
+    """harmonic_interpolation_b200.poisson.gradient_rhs (vectorised G.T u with mask borders cut) against the oracle's
+    assembled gradient operator (poisson.py:204-251)."""
+    from harmonic_interpolation_b200 import poisson as P
+    from oracle import grid_oracle as go
+    rng = np.random.default_rng(4)
+    for rows, cols, K, with_mask in ((7, 9, 1, False), (12, 5, 3, True), (1, 6, 2, False), (6, 1, 1, True)):
+        u = rng.normal(size=(rows, cols, 2, K))
+        mask = None
+        if with_mask:
+            mask = rng.random((rows, cols)) < 0.7
+        got, down, right = P.gradient_rhs(u, mask)
+        G = go.gradient_operator(rows, cols, mask)
+        want = (G.T @ u.reshape(rows * cols * 2, K)).reshape(rows, cols, K)
+        assert np.abs(got - want).max() < 1e-13
+        # the edges that exist are exactly the rows of G that are not empty
+        nz = np.asarray(abs(G).sum(axis=1)).ravel().reshape(rows, cols, 2) > 0
+        assert (nz[:, :, 0] == down).all() and (nz[:, :, 1] == right).all()
