@@ -172,10 +172,10 @@ def main():
         return
 
     # A multi-rank run that stops making progress (rendezvous, NCCL bootstrap, a collective one rank never enters)
-    # must not sit on N GPUs until somebody else's limit kills it: after HGRID_BENCH_WATCHDOG seconds (default 300; a normal run takes about a minute)
+    # must not sit on N GPUs until somebody else's limit kills it: after HGRID_BENCH_WATCHDOG seconds (default 420; a normal run takes one to two minutes)
     # every rank dumps its Python stacks to stderr and exits.
     import faulthandler
-    faulthandler.dump_traceback_later(int(os.environ.get("HGRID_BENCH_WATCHDOG", 300)), exit=True)
+    faulthandler.dump_traceback_later(int(os.environ.get("HGRID_BENCH_WATCHDOG", 420)), exit=True)
 
     import torch
     import torch.distributed as dist
