@@ -174,6 +174,10 @@ def main():
     # A multi-rank run that stops making progress (rendezvous, NCCL bootstrap, a collective one rank never enters)
     # must not sit on N GPUs until somebody else's limit kills it: after HGRID_BENCH_WATCHDOG seconds (default 420; a normal run takes one to two minutes)
     # every rank dumps its Python stacks to stderr and exits.
+    # The collectives of this path are tiny (K doubles, a few MB of ghost rows): NVLink SHARP (NVLS) buys nothing and its
+    # multicast set-up is one more thing that can go wrong when communicators of different sizes are created back to back.
+    if world > 1:
+        os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
     import faulthandler
     faulthandler.dump_traceback_later(int(os.environ.get("HGRID_BENCH_WATCHDOG", 420)), exit=True)
 
