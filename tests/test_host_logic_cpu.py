@@ -49,3 +49,46 @@ def test_poisson_gradient_rhs_matches_the_gradient_operator():
         # the edges that exist are exactly the rows of G that are not empty
         nz = np.asarray(abs(G).sum(axis=1)).ravel().reshape(rows, cols, 2) > 0
         assert (nz[:, :, 0] == down).all() and (nz[:, :, 1] == right).all()
+
+
+def test_cli_argument_errors_exit_minus_one(tmp_path, capsys):
+    """fill_alpha_harmonic.py:47-69: wrong argument count, missing input, existing output -> usage text and exit(-1),
+    before any GPU work."""
+    import pytest
+    from harmonic_interpolation_b200 import fill_alpha_harmonic as F
+    from conftest import GOLDEN
+    import os
+    inp = os.path.join(GOLDEN, "fill_alpha_harmonic_test.png")
+    existing = tmp_path / "out.png"
+    existing.write_bytes(b"x")
+    for argv in (["prog"], ["prog", inp], ["prog", inp, "a", "b"], ["prog", str(tmp_path / "missing.png"), str(tmp_path / "o.png")],
+                 ["prog", inp, str(existing)]):
+        with pytest.raises(SystemExit) as e:
+            F.main(argv)
+        assert e.value.code == -1
+        assert "Usage:" in capsys.readouterr().err
+
+
+def test_constraint_array_forms_match_tuple_forms():
+    """The array forms of the constraint arguments (extension) encode exactly what the tuple forms do."""
+    rng = np.random.default_rng(9)
+    rows, cols = 11, 14
+    ij = np.unique(np.stack([rng.integers(0, rows - 1, 30), rng.integers(0, cols - 1, 30)], 1), axis=0)
+    vals = rng.normal(size=len(ij))
+    tup = [(int(i), int(j), float(v)) for (i, j), v in zip(ij, vals)]
+    i1, v1 = R._scalar_constraints(tup, rows, cols, rows - 1, cols)
+    i2, v2 = R._scalar_constraints((ij, vals), rows, cols, rows - 1, cols)
+    mask = np.zeros((rows, cols), bool); mask[tuple(ij.T)] = True
+    dense = np.zeros((rows, cols)); dense[tuple(ij.T)] = vals
+    i3, v3 = R._scalar_constraints((mask, dense), rows, cols, rows - 1, cols)
+    o1, o2, o3 = np.argsort(i1), np.argsort(i2), np.argsort(i3)
+    assert (i1[o1] == i2[o2]).all() and (i1[o1] == i3[o3]).all()
+    assert np.allclose(v1[o1], v2[o2]) and np.allclose(v1[o1], v3[o3])
+    # cut edges: list of pairs, (n,4) array, pair of planes
+    m = rng.random((rows, cols)) < 0.4
+    edges = R.cut_edges_from_mask(m)
+    arr = np.asarray([(a[0], a[1], b[0], b[1]) for a, b in edges])
+    planes = R.cut_planes_from_mask(m)
+    a = R._cut_planes(rows, cols, edges); b = R._cut_planes(rows, cols, arr); c = R._cut_planes(rows, cols, planes)
+    for x in (b, c):
+        assert (a[0] == x[0]).all() and (a[1] == x[1]).all() and a[2] == x[2]
