@@ -224,6 +224,13 @@ struct Solver : SolverBase {
         phase_ev.clear(); phase_id.clear();
     }
     bool exchange_p = getenv("HGRID_EXCHANGE_P") != nullptr;
+    // HGRID_OVERLAP=1 (slab mode; written after round 1's GPU budget was spent, NOT YET RUN on a GPU -- off by default):
+    // the 128-row exchange of r at the head of the V-cycle travels on a second stream while the downward leg works
+    // on the chunks that read no ghost row; the chunks next to the ghost bands follow once the rows have arrived.
+    bool overlap = getenv("HGRID_OVERLAP") != nullptr;
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_arrived = nullptr;
+    int sl_n_int[2] = {0, 0};          // down lists (lean, general): number of interior tasks, which come first
     bool no_fuse = getenv("HGRID_FUSE") == nullptr;      // the fused loop is opt-in (HGRID_FUSE=1): it does not pay yet
     int sl_ns = 0, sl_nt = 0;
     int* d_sl_tasks = nullptr;
@@ -255,6 +262,9 @@ struct Solver : SolverBase {
         if (comm && g_nccl.ok) g_nccl.CommDestroy(comm);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (stream2) cudaStreamDestroy(stream2);
+        if (ev_ready) cudaEventDestroy(ev_ready);
+        if (ev_arrived) cudaEventDestroy(ev_arrived);
         if (stream) cudaStreamDestroy(stream);
     }
 
@@ -262,6 +272,11 @@ struct Solver : SolverBase {
         CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CU(cudaEventCreate(&ev0));
         CU(cudaEventCreate(&ev1));
+        if (overlap) {
+            CU(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&ev_arrived, cudaEventDisableTiming));
+        }
         CU(cudaMalloc(&d_flags, plane));
         CU(cudaMalloc(&d_state, sizeof(CgState)));
         CU(cudaMalloc(&d_presum, (size_t)HG_MAXK * PRESUM_BLOCKS * sizeof(double)));
@@ -759,8 +774,18 @@ struct Solver : SolverBase {
                 const std::vector<uint8_t>& a = which < 2 ? hd : hu;
                 const uint8_t want = (which & 1) ? 2 : 1;
                 sl_off[which] = (int)lists.size();
+                // a down task is a boundary task if its rows 64 t - 3 .. 64 t + 66 touch a ghost band
+                auto boundary = [&](int e) {
+                    const int t = e / sl_ns;
+                    return (ghost_top > 0 && SL_R * t - 3 < ghost_top) || (ghost_bottom > 0 && SL_R * t + SL_R + 2 >= rows - ghost_bottom);
+                };
+                const bool split = overlap && world > 1 && which < 2;
                 for (int e = 0; e < n; ++e)
-                    if (a[e] == want) lists.push_back(e);
+                    if (a[e] == want && !(split && boundary(e))) lists.push_back(e);
+                if (which < 2) sl_n_int[which] = (int)lists.size() - sl_off[which];
+                if (split)
+                    for (int e = 0; e < n; ++e)
+                        if (a[e] == want && boundary(e)) lists.push_back(e);
                 *cnt[which] = (int)lists.size() - sl_off[which];
             }
             cudaFree(d_sl_tasks);
@@ -895,6 +920,16 @@ struct Solver : SolverBase {
         const Grid<T> g = grid();
         const int nl = (int)coarse.size();
         if (nl > 0) {
+            if (world > 1 && overlap && stream_legs() && !fuse_r_old) {
+                CU(cudaEventRecord(ev_ready, stream));               // r is final on the owned rows
+                CU(cudaStreamWaitEvent(stream2, ev_ready, 0));
+                HGTRY(exchange(r, HG_GHOST_ROWS, stream2));
+                CU(cudaEventRecord(ev_arrived, stream2));
+                launch_sl_down(g, r, coarse[0], done, 1);            // chunks that read no ghost row
+                CU(cudaStreamWaitEvent(stream, ev_arrived, 0));
+                launch_sl_down(g, r, coarse[0], done, 2);            // chunks next to the ghost bands
+                mark(3);
+            } else {
             if (world > 1) HGTRY(exchange(r, HG_GHOST_ROWS));
             if (fuse_r_old) {
                 launch_sl_down_fused(g, fuse_r_old, r, coarse[0], done);
@@ -903,6 +938,7 @@ struct Solver : SolverBase {
             else if (has_pen) mg_down0_kernel<T, true><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, DOWN_H, true>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
             else if (scalar_legs) mg_down0_kernel<T, false><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, DOWN_H, false>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
             else mg_down0v_kernel<T><<<tile_grid(), VR_THREADS, sizeof(VRegionSmem<T>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
+            }
             ++launches;
             if (world == 1) {
                 coarse_vcycle(coarse, d_dense, done);
@@ -947,16 +983,19 @@ struct Solver : SolverBase {
     dim3 sl_grid(int ntasks) const { return dim3((unsigned)(((long long)ntasks * K + SL_WPB - 1) / SL_WPB)); }
     dim3 sl_block() const { return dim3(32 * SL_WPB); }
     size_t sl_smem() const { return (size_t)SL_WPB * SL_RING * 128 * sizeof(T); }   // lean kernels: one ring of rows per warp
-    void launch_sl_down(const Grid<T>& g, const T* r, const Coarse<T>& c1, const int* done) {
+    // part 0: every task; 1: the interior tasks (front of the lists); 2: the boundary tasks (HGRID_OVERLAP)
+    void launch_sl_down(const Grid<T>& g, const T* r, const Coarse<T>& c1, const int* done, int part = 0) {
         const int zx = unfused_coarse ? 1 : 0;
         const SlFuse nf = {nullptr, nullptr, nullptr, nullptr, 0};
-        if (sl_n_down_lean)
-            sl_down_kernel<T, false, true><<<sl_grid(sl_n_down_lean), sl_block(), sl_smem(), stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[0], sl_n_down_lean, sl_ns, zx, done, nf);
-        if (sl_n_down_gen) {
-            if (has_soft()) sl_down_kernel<T, true, false><<<sl_grid(sl_n_down_gen), sl_block(), 0, stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[1], sl_n_down_gen, sl_ns, zx, done, nf);
-            else sl_down_kernel<T, false, false><<<sl_grid(sl_n_down_gen), sl_block(), 0, stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[1], sl_n_down_gen, sl_ns, zx, done, nf);
+        const int o_l = part == 2 ? sl_n_int[0] : 0, n_l = part == 1 ? sl_n_int[0] : sl_n_down_lean - o_l;
+        const int o_g = part == 2 ? sl_n_int[1] : 0, n_g = part == 1 ? sl_n_int[1] : sl_n_down_gen - o_g;
+        if (n_l > 0)
+            sl_down_kernel<T, false, true><<<sl_grid(n_l), sl_block(), sl_smem(), stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[0] + o_l, n_l, sl_ns, zx, done, nf);
+        if (n_g > 0) {
+            if (has_soft()) sl_down_kernel<T, true, false><<<sl_grid(n_g), sl_block(), 0, stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[1] + o_g, n_g, sl_ns, zx, done, nf);
+            else sl_down_kernel<T, false, false><<<sl_grid(n_g), sl_block(), 0, stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[1] + o_g, n_g, sl_ns, zx, done, nf);
         }
-        launches += (sl_n_down_lean > 0) + (sl_n_down_gen > 0) - 1;
+        launches += (n_l > 0) + (n_g > 0) - (part == 2 ? 0 : 1);
     }
     // the same leg with the CG update fused in: r_new = r_old - alpha q (to `r_new`), partial sums of r_new.r_new
     void launch_sl_down_fused(const Grid<T>& g, const T* r_old, T* r_new, const Coarse<T>& c1, const int* done) {
@@ -1242,8 +1281,9 @@ struct Solver : SolverBase {
     // refresh `depth_t` / `depth_b` ghost rows of the planes of `v` from the neighbours' owned rows
     // (level geometry given by pitch_, plane_, rows_, and the ghost-band depths gt_, gb_ at that level)
     template <typename V>
-    int exchange_rows(V* v, int nplanes, int pitch_, long long plane_, int rows_, int gt_, int gb_, int depth) {
+    int exchange_rows(V* v, int nplanes, int pitch_, long long plane_, int rows_, int gt_, int gb_, int depth, cudaStream_t xs = nullptr) {
         if (world <= 1) return HG_OK;
+        cudaStream_t stream = xs ? xs : this->stream;
         const ncclDataType_t dt = sizeof(V) == 8 ? ncclDouble : ncclFloat;
         NC(g_nccl.GroupStart());
         for (int k = 0; k < nplanes; ++k) {
@@ -1264,7 +1304,7 @@ struct Solver : SolverBase {
     }
     // level-0 vector, `depth` ghost rows
     template <typename V>
-    int exchange(V* v, int depth) { return exchange_rows(v, K, pitch, plane, rows, ghost_top, ghost_bottom, depth); }
+    int exchange(V* v, int depth, cudaStream_t xs = nullptr) { return exchange_rows(v, K, pitch, plane, rows, ghost_top, ghost_bottom, depth, xs); }
     template <typename V>
     int exchange_level(const Coarse<T>& L, int level, V* v, int nplanes) {
         return exchange_rows(v, nplanes, L.pitch, L.plane, L.rows, ghost_top >> level, ghost_bottom >> level, HG_GHOST_ROWS);
