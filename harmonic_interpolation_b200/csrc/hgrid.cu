@@ -176,6 +176,8 @@ struct Solver : SolverBase {
     std::vector<Lev25<T>> lev25;
     double* d_dense25 = nullptr;
     int mg25_sweeps = getenv("HGRID_MG25_SWEEPS") ? atoi(getenv("HGRID_MG25_SWEEPS")) : 1;
+    bool mg25_rowgs = getenv("HGRID_MG25_ROWGS") != nullptr;    // row-coloured smoother (mg25.cuh): not yet run on a GPU, opt-in
+    T* d_z2 = nullptr;                                           // level-0 half of its double buffer
     // finest levels that get the aggregate correction (experimental, off by default: it cuts the iteration count 4x at
     // 256^2 but does not scale -- at 2048^2 the undamped additive step on densely coupled clusters costs iterations)
     int mg25_agg_levels = getenv("HGRID_MG25_AGG") ? atoi(getenv("HGRID_MG25_AGG")) : 0;
@@ -409,11 +411,13 @@ struct Solver : SolverBase {
         d_dense = d_gdense = nullptr;
         for (size_t l = 0; l < lev25.size(); ++l) {
             cudaFree(lev25[l].coef); cudaFree(lev25[l].label); cudaFree(lev25[l].aggD); cudaFree(lev25[l].aggS);
-            if (l > 0) { cudaFree(lev25[l].x); cudaFree(lev25[l].b); }
+            if (l > 0) { cudaFree(lev25[l].x); cudaFree(lev25[l].b); cudaFree(lev25[l].x2); }
         }
         lev25.clear();
         cudaFree(d_dense25);
         d_dense25 = nullptr;
+        cudaFree(d_z2);
+        d_z2 = nullptr;
     }
 
     static int chain(int n, int levels) { for (int l = 0; l < levels; ++l) n = (n + 1) / 2; return n; }
@@ -621,7 +625,15 @@ struct Solver : SolverBase {
             L.K = K;
             L.coef = L.x = L.b = nullptr;
             L.label = nullptr; L.aggD = nullptr; L.aggS = nullptr;
+            L.x2 = nullptr;
             CU(cudaMalloc(&L.coef, (size_t)L.plane * 25 * sizeof(T)));
+            if (mg25_rowgs) {
+                T* alt = nullptr;
+                CU(cudaMalloc(&alt, (size_t)L.plane * K * sizeof(T)));
+                CU(cudaMemsetAsync(alt, 0, (size_t)L.plane * K * sizeof(T), stream));
+                if (level == 0) d_z2 = alt;
+                L.x2 = alt;
+            }
             if (level > 0) {
                 CU(cudaMalloc(&L.x, (size_t)L.plane * K * sizeof(T)));
                 CU(cudaMalloc(&L.b, (size_t)L.plane * K * sizeof(T)));
@@ -695,7 +707,17 @@ struct Solver : SolverBase {
         agg_apply_kernel<T><<<pg, 256, 0, stream>>>(L, done);
         launches += 3;
     }
-    void gs25(const Lev25<T>& L, bool forward, const int* done) {
+    void gs25(Lev25<T>& L, bool forward, const int* done) {
+        if (mg25_rowgs && L.x2) {
+            // one launch per row colour; the iterate moves from L.x to L.x2, then the two swap roles
+            dim3 rg((L.cols + RG_SEG - 1) / RG_SEG, (L.rows + 2) / 3);
+            for (int s = 0; s < mg25_sweeps; ++s) {
+                for (int c = 0; c < 3; ++c) gs25_rows_kernel<T><<<rg, RG_THREADS, 0, stream>>>(L, L.x, L.x2, forward ? c : 2 - c, forward ? 1 : 0, done);
+                std::swap(L.x, L.x2);
+            }
+            launches += 3 * mg25_sweeps;
+            return;
+        }
         dim3 gg(((L.cols + 2) / 3 + 127) / 128, (L.rows + 2) / 3);
         for (int s = 0; s < mg25_sweeps; ++s)
             for (int c = 0; c < 9; ++c) gs25_kernel<T><<<gg, 128, 0, stream>>>(L, forward ? c : 8 - c, done);
@@ -704,6 +726,7 @@ struct Solver : SolverBase {
     // z = M^-1 r: one symmetric V-cycle from the zero guess on the 25-point hierarchy (level 0 works in place on z, r)
     int vcycle25(T* z, T* r, const int* done) {
         lev25[0].x = z; lev25[0].b = r;
+        if (mg25_rowgs) lev25[0].x2 = d_z2;
         CU(cudaMemsetAsync(z, 0, (size_t)plane * K * sizeof(T), stream));
         const int n = (int)lev25.size();
         for (int l = 0; l + 1 < n; ++l) {
@@ -720,6 +743,8 @@ struct Solver : SolverBase {
             gs25(lev25[l], false, done);
         }
         launches += 2 * (n - 1) + 2;
+        // the double-buffered smoother may leave the result in the other buffer (odd number of sweeps in total)
+        if (lev25[0].x != z) CU(cudaMemcpyAsync(z, lev25[0].x, (size_t)plane * K * sizeof(T), cudaMemcpyDeviceToDevice, stream));
         return HG_OK;
     }
 

@@ -29,6 +29,7 @@ struct Lev25 {
     T* coef;   // 25 planes, plane (di + 2) * 5 + (dj + 2); a pixel whose centre coefficient is 0 is inactive
     T* x;      // K planes
     T* b;      // K planes
+    T* x2;     // K planes: the other half of the double buffer of the row-coloured smoother (gs25_rows_kernel), else nullptr
     // aggregate correction for stiff couplings (finest levels only; nullptr elsewhere)
     int* label;      // cluster root (a pixel index) of every pixel that has a strong coupling, -1 otherwise
     double* aggD;    // at root pixels: sum of the cluster's block of A (v^T A v for the cluster's indicator v)
@@ -426,6 +427,73 @@ agg_apply_kernel(Lev25<T> L, const int* __restrict__ done) {
     const double d = L.aggD[lab];
     if (!(d > 0.0)) return;
     for (int k = 0; k < L.K; ++k) L.x[k * L.plane + o] += (T)(L.aggS[k * L.plane + lab] / d);
+}
+
+// ---- row-coloured Gauss-Seidel: one launch per ROW colour, the three column colours inside the block -------------
+// (HGRID_MG25_ROWGS=1; written after round 1's GPU budget was spent: compiled, NOT YET RUN on a GPU, off by default.)
+// The nine launches of gs25_kernel each touch every third pixel of every third row, so every 32-byte sector of the
+// 25 coefficient planes is fetched three times per sweep.  Here a block owns a segment of one row i = ci (mod 3) and
+// sweeps its three column colours in sequence, keeping the row in shared memory: the coefficients of the segment
+// come from DRAM once and from L1 / L2 twice.  Same-row dependencies across segment borders are met by recomputing
+// RG_H = 4 halo pixels on either side (first colour on s0-4 .. s1+4, second on s0-2 .. s1+2, third on the segment).
+// To keep that recomputation race-free the iterate is double-buffered: a launch reads the rows it sweeps, and the
+// rows not yet swept in this sweep, from `xin`, the rows already swept from `xout`, and writes `xout` only.  After
+// the three launches `xout` holds the whole new iterate.  The ordering is exactly that of the nine-colour sweep.
+#define RG_SEG 384
+#define RG_THREADS 128
+#define RG_H 4
+template <typename T>
+__global__ void __launch_bounds__(RG_THREADS)
+gs25_rows_kernel(Lev25<T> L, const T* __restrict__ xin, T* __restrict__ xout, int ci, int forward, const int* __restrict__ done) {
+    if (done && *done) return;
+    __shared__ T xs[RG_SEG + 2 * RG_H + 4];            // columns s0 - RG_H - 2 .. s0 + RG_SEG + RG_H + 1 of the row
+    const int i = 3 * blockIdx.y + ci;
+    if (i >= L.rows) return;
+    const int s0 = blockIdx.x * RG_SEG, s1 = min(s0 + RG_SEG, L.cols);
+    const int lo = s0 - RG_H - 2, nx = RG_SEG + 2 * RG_H + 4;
+    const long long orow = (long long)i * L.pitch;
+    for (int k = 0; k < L.K; ++k) {
+        const T* xi = xin + k * L.plane;
+        T* xo = xout + k * L.plane;
+        const T* bk = L.b + k * L.plane;
+        __syncthreads();
+        for (int e = threadIdx.x; e < nx; e += RG_THREADS) {
+            const int j = lo + e;
+            xs[e] = (j >= 0 && j < L.cols) ? xi[orow + j] : T(0);
+        }
+        __syncthreads();
+        for (int step = 0; step < 3; ++step) {
+            const int c = forward ? step : 2 - step;
+            const int h = RG_H - 2 * step;              // this colour is needed (and valid) on s0 - h .. s1 + h - 1
+            const int first = s0 - h;
+            const int jstart = first + ((c - (first % 3 + 3) % 3) + 3) % 3;
+            for (int j = jstart + 3 * (int)threadIdx.x; j < s1 + h; j += 3 * RG_THREADS) {
+                if (j < 0 || j >= L.cols) continue;
+                const long long o = orow + j;
+                const T c12 = L.coef[12 * L.plane + o];
+                if (!(c12 > T(0))) continue;
+                T v = bk[o];
+#pragma unroll
+                for (int di = -2; di <= 2; ++di) {
+                    // rows i + di, di != 0, have the other two row colours: swept already in this sweep?
+                    const int cr = ((ci + di) % 3 + 3) % 3;
+                    const bool swept = forward ? cr < ci : cr > ci;
+                    const T* src = swept ? xo : xi;
+#pragma unroll
+                    for (int dj = -2; dj <= 2; ++dj) {
+                        const int cc = (di + 2) * 5 + (dj + 2);
+                        if (cc == 12) continue;
+                        const T a = L.coef[cc * L.plane + o];
+                        if (a == T(0)) continue;                     // also: neighbours outside the grid
+                        v -= a * (di == 0 ? xs[j + dj - lo] : src[o + (long long)di * L.pitch + dj]);
+                    }
+                }
+                xs[j - lo] = v / c12;
+            }
+            __syncthreads();
+        }
+        for (int j = s0 + (int)threadIdx.x; j < s1; j += RG_THREADS) xo[orow + j] = xs[j - lo];
+    }
 }
 
 }  // namespace hg
