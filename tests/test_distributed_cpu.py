@@ -51,7 +51,7 @@ def _worker(rank, world, port, rows, cols, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 4])
 def test_ghost_rows_over_gloo(world):
     port = _free_port()
     ctx = mp.get_context("spawn")
