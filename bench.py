@@ -274,7 +274,7 @@ def main():
     # DRAM traffic of that kernel per launch from the committed `ncu --set full` capture of this workload
     traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    kname = "sl_lap_kernel<%s, 0>" % ("float" if W == 4 else "double")
+    kname = "sl_lap_kernel<%s, %s, 0, 0>" % (("float", "float") if W == 4 else ("double", "double"))
     if os.path.isfile(tp) and n == 16384 and world == 1:
         ent = json.load(open(tp)).get(kname)
         if ent:
@@ -301,7 +301,7 @@ def main():
                 "seconds_per_step": float(t_e2e.item()),
                 "api": "hg_solve_u8 via SlabSolver.solve_u8: uint8 RGB in pinned host memory -> uint8 RGB (pattern uploaded once, as with the reference's factor-once closure)"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": kname + "  (q = A p and the partial sums of p.q: the stencil launch of every CG iteration; + its general-chunk twin sl_lap_kernel<.., 1> on the 2 % of chunks that touch the grid border)",
+        "roofline": {"bound": "hbm", "kernel": kname + "  (q = A p and the partial sums of p.q: the stencil launch of every CG iteration; + its general-chunk twin sl_lap_kernel<.., 1, 0> on the 2 % of chunks that touch the grid border)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_apply, "peak_source": peak_src,
