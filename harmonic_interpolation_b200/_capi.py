@@ -16,7 +16,7 @@ EDGES_REFERENCE, EDGES_UNIFORM = 0, 1
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_UNREFERENCED, ERR_EMPTY_ROWS = -1, -2, -3, -4, -5
-ERR_NOT_CONVERGED, ERR_BREAKDOWN, ERR_NOMEM = -6, -7, -8
+ERR_NOT_CONVERGED, ERR_BREAKDOWN, ERR_NOMEM, ERR_COMM = -6, -7, -8, -9
 
 _dp = ctypes.POINTER(ctypes.c_double)
 
@@ -63,11 +63,17 @@ SYMBOLS = {
     "hg_comm_unique_id": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint8)]),
     "hg_comm_init": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                     ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    "hg_set_phase_timing": (ctypes.c_int, [_H, ctypes.c_int]),
+    "hg_get_phase_ms": (ctypes.c_int, [_H, _dp, ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
     "hg_bench_apply": (ctypes.c_int, [_H, ctypes.c_int, _dp]),
     "hg_precond_apply": (ctypes.c_int, [_H, _dp, _dp]),
     "hg_mg_levels": (ctypes.c_int, [_H]),
     "hg_mg_get_level": (ctypes.c_int, [_H, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), _dp]),
 }
+
+N_PHASES = 10
+PHASE_NAMES = ["other", "stencil+alpha", "x/r update+check", "fine down", "level-1 down", "levels>=2", "level-1 up", "fine up",
+               "beta+p update", "outer residual"]
 
 _lib = None
 

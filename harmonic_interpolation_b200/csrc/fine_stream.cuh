@@ -282,6 +282,9 @@ struct SlLean {
     }
     // request row i of r into slot `slot` (zeros where the quad has no free pixel); one commit group per row
     __device__ __forceinline__ void request(int i, int slot, unsigned m) {
+        // (a caller's mask may come from the NEIGHBOURING rows -- SlLap MODE 1 -- so the row itself is checked here:
+        // rows -1 and `rows` lie outside the plane, for the first / last channel outside the allocation)
+        if ((unsigned)i >= (unsigned)rows || !colin) m = 0u;
         const T* src = rk + (m ? i * pitch + c0 : 0);
         T* dst = ring + slot * 128;
         sl_cp16(dst, src, m != 0u);

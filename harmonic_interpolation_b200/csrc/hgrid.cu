@@ -4,6 +4,7 @@
 #include <nccl.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <new>
@@ -57,6 +58,8 @@ struct Nccl {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t*) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -83,6 +86,8 @@ static int nccl_load() {
     HG_SYM(GetUniqueId, "ncclGetUniqueId");
     HG_SYM(CommInitRank, "ncclCommInitRank");
     HG_SYM(CommDestroy, "ncclCommDestroy");
+    HG_SYM(CommAbort, "ncclCommAbort");
+    HG_SYM(CommGetAsyncError, "ncclCommGetAsyncError");
     HG_SYM(AllReduce, "ncclAllReduce");
     HG_SYM(Send, "ncclSend");
     HG_SYM(Recv, "ncclRecv");
@@ -126,6 +131,8 @@ struct SolverBase {
     virtual int upload_u8(const uint8_t* vals, hg_stats* st) = 0;
     virtual int download_u8(uint8_t* out, hg_stats* st) = 0;
     virtual int comm_init(const uint8_t* id, int rank, int world, int ghost_top, int ghost_bottom, const int* row_starts, int global_rows) = 0;
+    virtual int set_phase_timing(int on) = 0;
+    virtual int get_phase_ms(double* ms, int* counts, int n) = 0;
 };
 
 template <typename T>
@@ -198,10 +205,14 @@ struct Solver : SolverBase {
     // per-chunk partial sums of r.r
     T *d_p2 = nullptr, *d_r2 = nullptr;
     double* d_spart3 = nullptr;
-    // HGRID_PHASES=1: CUDA-event time of the phases of the MG-PCG loop, printed to stderr after the solve (debug aid)
-    bool phase_timing = getenv("HGRID_PHASES") != nullptr;
+    // Phase timing (hg_set_phase_timing, or HGRID_PHASES=1 which also prints to stderr): CUDA events on the solver's
+    // stream between the launches of the MG-PCG loop; totals per phase of the last solve are kept for hg_get_phase_ms.
+    bool phase_print = getenv("HGRID_PHASES") != nullptr;
+    bool phase_timing = phase_print;
     std::vector<cudaEvent_t> phase_ev;
     std::vector<int> phase_id;
+    double phase_tot[HG_N_PHASES] = {0};
+    int phase_cnt[HG_N_PHASES] = {0};
     void mark(int id) {
         if (!phase_timing) return;
         cudaEvent_t e;
@@ -211,19 +222,28 @@ struct Solver : SolverBase {
         phase_id.push_back(id);
     }
     void report_phases() {
+        for (int k = 0; k < HG_N_PHASES; ++k) { phase_tot[k] = 0.0; phase_cnt[k] = 0; }
         if (!phase_timing || phase_ev.empty()) return;
-        static const char* names[] = {"start", "p-exchange + stencil + alpha", "x/r update + check", "V-cycle: fine down", "V-cycle: coarse levels", "V-cycle: fine up", "beta + p update", "outer residual"};
-        double tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (size_t i = 1; i < phase_ev.size(); ++i) {
             float ms = 0;
             cudaEventElapsedTime(&ms, phase_ev[i - 1], phase_ev[i]);
-            tot[phase_id[i]] += ms;
+            phase_tot[phase_id[i]] += ms;
+            phase_cnt[phase_id[i]] += 1;
         }
-        fprintf(stderr, "[hgrid rank %d] phases (ms):", rank);
-        for (int k = 1; k < 8; ++k) fprintf(stderr, "  %s %.2f |", names[k], tot[k]);
-        fprintf(stderr, "\n");
+        if (phase_print) {
+            static const char* names[HG_N_PHASES] = {"(other)", "stencil + alpha", "x/r update + check", "fine down", "level-1 down", "levels >= 2",
+                                                     "level-1 up", "fine up", "beta + p update", "outer residual"};
+            fprintf(stderr, "[hgrid rank %d] phases (ms):", rank);
+            for (int k = 1; k < HG_N_PHASES; ++k) fprintf(stderr, "  %s %.2f (%d) |", names[k], phase_tot[k], phase_cnt[k]);
+            fprintf(stderr, "\n");
+        }
         for (auto e : phase_ev) cudaEventDestroy(e);
         phase_ev.clear(); phase_id.clear();
+    }
+    int set_phase_timing(int on) override { phase_timing = on != 0 || phase_print; return HG_OK; }
+    int get_phase_ms(double* ms, int* counts, int n) override {
+        for (int k = 0; k < n && k < HG_N_PHASES; ++k) { if (ms) ms[k] = phase_tot[k]; if (counts) counts[k] = phase_cnt[k]; }
+        return HG_OK;
     }
     bool exchange_p = getenv("HGRID_EXCHANGE_P") != nullptr;
     // HGRID_OVERLAP=1 (slab mode; written after round 1's GPU budget was spent, NOT YET RUN on a GPU -- off by default):
@@ -582,7 +602,7 @@ struct Solver : SolverBase {
             for (int q = 0; q < world; ++q) { gl[2 * q] = gl_start(q); gl[2 * q + 1] = gl_end(q) - gl_start(q); }
             if (!d_gl_rows) CU(cudaMalloc(&d_gl_rows, 2 * world * sizeof(int)));
             CU(cudaMemcpyAsync(d_gl_rows, gl.data(), 2 * world * sizeof(int), cudaMemcpyHostToDevice, stream));
-            CU(cudaStreamSynchronize(stream));
+            HGTRY(sync_watchful());
         }
         const Coarse<T>& Ll = coarse.back();      // local level HG_GATHER_LEVEL
         Coarse<T> G;
@@ -900,9 +920,17 @@ struct Solver : SolverBase {
     // V-cycle over levels[from..] of a hierarchy whose first level already holds b (and x = 0)
     void coarse_vcycle(const std::vector<Coarse<T>>& lv, const double* dense, const int* done) {
         const int n = (int)lv.size();
-        for (int l = 0; l + 1 < n; ++l) coarse_down(lv[l], lv[l + 1], done);
+        const bool top = &lv == &coarse;      // (marks: level 1 of the local hierarchy on its own)
+        for (int l = 0; l + 1 < n; ++l) {
+            coarse_down(lv[l], lv[l + 1], done);
+            if (top && l == 0) mark(HG_PH_L1_DOWN);
+        }
         coarse_solve(lv[n - 1], dense, done);
-        for (int l = n - 2; l >= 0; --l) coarse_up(lv[l], lv[l + 1], done);
+        for (int l = n - 2; l >= 0; --l) {
+            if (top && l == 0) mark(HG_PH_COARSE);
+            coarse_up(lv[l], lv[l + 1], done);
+            if (top && l == 0) mark(HG_PH_L1_UP);
+        }
     }
 
     // z = M^-1 r : one V(1,1) cycle from a zero initial guess; also leaves the per-tile partial
@@ -953,13 +981,13 @@ struct Solver : SolverBase {
                 launch_sl_down(g, r, coarse[0], done, 1);            // chunks that read no ghost row
                 CU(cudaStreamWaitEvent(stream, ev_arrived, 0));
                 launch_sl_down(g, r, coarse[0], done, 2);            // chunks next to the ghost bands
-                mark(3);
+                mark(HG_PH_FINE_DOWN);
             } else {
             if (world > 1) HGTRY(exchange(r, HG_GHOST_ROWS));
             if (fuse_r_old) {
                 launch_sl_down_fused(g, fuse_r_old, r, coarse[0], done);
                 HGTRY(stage_check(d_spart3, sl_ns * sl_nt, (long long)sl_ns * sl_nt));
-            } else if (stream_legs()) { launch_sl_down(g, r, coarse[0], done); mark(3); }
+            } else if (stream_legs()) { launch_sl_down(g, r, coarse[0], done); mark(HG_PH_FINE_DOWN); }
             else if (has_pen) mg_down0_kernel<T, true><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, DOWN_H, true>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
             else if (scalar_legs) mg_down0_kernel<T, false><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, DOWN_H, false>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
             else mg_down0v_kernel<T><<<tile_grid(), VR_THREADS, sizeof(VRegionSmem<T>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
@@ -972,6 +1000,7 @@ struct Solver : SolverBase {
                 for (int l = 0; l + 1 < Lg; ++l) {       // local levels 1 .. Lg-1
                     HGTRY(exchange_level(coarse[l], l + 1, coarse[l].b, K));
                     coarse_down(coarse[l], coarse[l + 1], done);
+                    if (l == 0) mark(HG_PH_L1_DOWN);
                 }
                 // level Lg: gather the owned rows of b, solve replicated, take back the local window of x
                 const Coarse<T>& Ll = coarse[Lg - 1];
@@ -985,7 +1014,9 @@ struct Solver : SolverBase {
                                        (size_t)Ll.plane * sizeof(T), cudaMemcpyDeviceToDevice, stream));
                 for (int l = Lg - 2; l >= 0; --l) {
                     if (l + 2 < Lg) HGTRY(exchange_level(coarse[l + 1], l + 2, coarse[l + 1].x, K));
+                    if (l == 0) mark(HG_PH_COARSE);
                     coarse_up(coarse[l], coarse[l + 1], done);
+                    if (l == 0) mark(HG_PH_L1_UP);
                 }
                 HGTRY(exchange_level(coarse[0], 1, coarse[0].x, K));
             }
@@ -993,8 +1024,8 @@ struct Solver : SolverBase {
         Coarse<T> c0;
         memset(&c0, 0, sizeof c0);
         if (nl > 0) c0 = coarse[0];
-        mark(4);
-        if (stream_legs()) { launch_sl_up(g, r, z, c0, nl > 0, done); mark(5); }
+        mark(HG_PH_COARSE);
+        if (stream_legs()) { launch_sl_up(g, r, z, c0, nl > 0, done); mark(HG_PH_FINE_UP); }
         else if (has_pen) mg_up0_kernel<T, true><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, UP_H, true>), stream>>>(g, d_code, r, z, c0, nl > 0, d_tile_active, part_rz, done);
         else if (scalar_legs) mg_up0_kernel<T, false><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, UP_H, false>), stream>>>(g, d_code, r, z, c0, nl > 0, d_tile_active, part_rz, done);
         else mg_up0v_kernel<T><<<tile_grid(), VR_THREADS, sizeof(VRegionSmem<T>), stream>>>(g, d_code, r, z, c0, nl > 0, d_tile_active, part_rz, done);
@@ -1165,7 +1196,7 @@ struct Solver : SolverBase {
         unsigned long long counts[8];
         CU(cudaMemcpyAsync(counts, d_counts, sizeof counts, cudaMemcpyDeviceToHost, stream));
         CU(cudaEventRecord(ev1, stream));
-        CU(cudaStreamSynchronize(stream));
+        HGTRY(sync_watchful());
         CU(cudaGetLastError());
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, ev0, ev1));
@@ -1311,20 +1342,23 @@ struct Solver : SolverBase {
         cudaStream_t stream = xs ? xs : this->stream;
         const ncclDataType_t dt = sizeof(V) == 8 ? ncclDouble : ncclFloat;
         NC(g_nccl.GroupStart());
-        for (int k = 0; k < nplanes; ++k) {
+        ncclResult_t bad = ncclSuccess;
+        auto note = [&](ncclResult_t r) { if (r != ncclSuccess && bad == ncclSuccess) bad = r; };
+        for (int k = 0; k < nplanes && bad == ncclSuccess; ++k) {
             V* base = v + (long long)k * plane_;
             if (gt_ > 0) {
                 const int d = std::min(depth, gt_);
-                NC(g_nccl.Send(base + (long long)gt_ * pitch_, (size_t)d * pitch_, dt, rank - 1, comm, stream));
-                NC(g_nccl.Recv(base + (long long)(gt_ - d) * pitch_, (size_t)d * pitch_, dt, rank - 1, comm, stream));
+                note(g_nccl.Send(base + (long long)gt_ * pitch_, (size_t)d * pitch_, dt, rank - 1, comm, stream));
+                note(g_nccl.Recv(base + (long long)(gt_ - d) * pitch_, (size_t)d * pitch_, dt, rank - 1, comm, stream));
             }
             if (gb_ > 0) {
                 const int d = std::min(depth, gb_);
-                NC(g_nccl.Send(base + (long long)(rows_ - gb_ - d) * pitch_, (size_t)d * pitch_, dt, rank + 1, comm, stream));
-                NC(g_nccl.Recv(base + (long long)(rows_ - gb_) * pitch_, (size_t)d * pitch_, dt, rank + 1, comm, stream));
+                note(g_nccl.Send(base + (long long)(rows_ - gb_ - d) * pitch_, (size_t)d * pitch_, dt, rank + 1, comm, stream));
+                note(g_nccl.Recv(base + (long long)(rows_ - gb_) * pitch_, (size_t)d * pitch_, dt, rank + 1, comm, stream));
             }
         }
-        NC(g_nccl.GroupEnd());
+        note(g_nccl.GroupEnd());       // the group is closed whatever happened inside it
+        NC(bad);
         return HG_OK;
     }
     // level-0 vector, `depth` ghost rows
@@ -1403,7 +1437,51 @@ struct Solver : SolverBase {
     //
     // Two kernel sets: the tile path (Laplacian + multigrid, fine.cuh: fused V-cycle legs, tile
     // skipping) and the flat path (bilaplacian, or Jacobi on request).
+    // ---- slab mode: failure handling -----------------------------------------------------------------
+    // A rank that fails must not leave its peers inside a collective for ever.  (1) Host syncs of the solve
+    // poll the stream and the communicator: an asynchronous NCCL error, or HGRID_COMM_TIMEOUT seconds (default
+    // 60; an iteration takes milliseconds) without progress, aborts the communicator and returns HG_ERR_COMM.
+    // (2) Any hard failure of a solve in slab mode aborts the communicator, which releases the peers' NCCL
+    // kernels; they then fail the same way within their own timeout.  A dead handle refuses further solves.
+    bool comm_dead = false;
+    void abort_comm() {
+        if (comm && g_nccl.ok) g_nccl.CommAbort(comm);
+        comm = nullptr;
+        comm_dead = true;
+    }
+    int sync_watchful() {
+        if (world <= 1 || !comm) { CU(cudaStreamSynchronize(stream)); return HG_OK; }
+        static const double limit = getenv("HGRID_COMM_TIMEOUT") ? atof(getenv("HGRID_COMM_TIMEOUT")) : 60.0;
+        timespec t0;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        for (long spin = 0;; ++spin) {
+            const cudaError_t q = cudaStreamQuery(stream);
+            if (q == cudaSuccess) return HG_OK;
+            if (q != cudaErrorNotReady) CU(q);
+            if ((spin & 1023) == 1023) {
+                ncclResult_t ar = ncclSuccess;
+                if (g_nccl.CommGetAsyncError(comm, &ar) != ncclSuccess || (ar != ncclSuccess && ar != ncclInProgress))
+                    return fail(HG_ERR_COMM, std::string("slab mode: asynchronous NCCL error: ") + g_nccl.GetErrorString(ar));
+                timespec t1;
+                clock_gettime(CLOCK_MONOTONIC, &t1);
+                if ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec) > limit)
+                    return fail(HG_ERR_COMM, "slab mode: no progress within HGRID_COMM_TIMEOUT seconds (a peer has failed or left the solve)");
+            }
+        }
+    }
     int solve_device(double rtol, int maxiter, hg_stats* st) override {
+        if (comm_dead) return fail(HG_ERR_COMM, "slab mode: the communicator of this solver was aborted after an earlier failure");
+        const int rc = solve_device_impl(rtol, maxiter, st);
+        // not converged / breakdown are collective outcomes (every rank sees the same all-reduced scalars)
+        if (world > 1 && rc != HG_OK && rc != HG_ERR_NOT_CONVERGED && rc != HG_ERR_BREAKDOWN) {
+            const std::string keep = g_err;
+            abort_comm();
+            g_err = keep;
+        }
+        return rc;
+    }
+
+    int solve_device_impl(double rtol, int maxiter, hg_stats* st) {
         if (!is_setup || !have_values) return fail(HG_ERR_INVALID, "hg_solve_device: values have not been uploaded");
         if (maxiter <= 0) maxiter = 100000;
         launches = 0;
@@ -1431,7 +1509,8 @@ struct Solver : SolverBase {
         T* e = kRefine ? d_x : reinterpret_cast<T*>(d_xm);   // the vector the inner CG updates
         // large grids: look at the state after every iteration (a sync costs microseconds, an
         // iteration milliseconds); small grids: enqueue batches, the surplus launches are no-ops
-        const long long npix = (long long)rows * cols;
+        // (the same decision on every slab: ranks must enqueue the same collectives)
+        const long long npix = (long long)(world > 1 ? global_rows : rows) * cols;
         const int batch = npix >= (1LL << 22) ? 1 : ((mg || mg25) ? 4 : 32);
         const int nt = mg ? ntiles() : 0;
 
@@ -1462,8 +1541,9 @@ struct Solver : SolverBase {
                 HGTRY(stage_outer(d_part0, nb_op, nb_op, outer == 0, inner_red * inner_red));
             }
             launches += 2;
+            mark(HG_PH_OUTER);
             CU(cudaMemcpyAsync(&host, d_state, sizeof host, cudaMemcpyDeviceToHost, stream));
-            CU(cudaStreamSynchronize(stream));
+            HGTRY(sync_watchful());
             if (host.done) break;                                   // converged (1), NaN (2) or out of iterations (4)
             if (outer >= max_outer) break;
             // a refinement step that did not gain a factor 4 has hit the attainable accuracy
@@ -1507,20 +1587,20 @@ struct Solver : SolverBase {
                         HGTRY(stage_beta_rz(0));
                         launches += 3;
                     } else if (mg) {
-                        mark(0);
+                        mark(HG_PH_OTHER);
                         // (no exchange of p: its ghost rows are computed redundantly from z and the old p, and are
                         // valid next to the owned band just as the ghost rows of z are; HGRID_EXCHANGE_P=1 restores it)
                         if (exchange_p) HGTRY(exchange(d_p, 1));
                         HGTRY(lap_and_alpha(d_p, d_q, done));
                         launches -= 2;
-                        mark(1);
+                        mark(HG_PH_STENCIL);
                         cg_update_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, e, d_r, d_p, d_q, d_tile_active, d_tpart0);
                         HGTRY(stage_check(tile_part(d_tpart0), n_own_tiles(), nt));
-                        mark(2);
+                        mark(HG_PH_UPDATE);
                         HGTRY(vcycle(d_z, d_r, done, d_tpart1));
                         HGTRY(stage_beta_rz(0));
                         cg_pupdate_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, d_p, d_z, d_tile_active, 0);
-                        mark(6);
+                        mark(HG_PH_PUPDATE);
                         launches += 6;
                     } else {
                         launch_op<0, 1>(d_p, nullptr, d_q, d_part0, done);
@@ -1536,7 +1616,7 @@ struct Solver : SolverBase {
                     }
                 }
                 CU(cudaMemcpyAsync(&host, d_state, sizeof host, cudaMemcpyDeviceToHost, stream));
-                CU(cudaStreamSynchronize(stream));
+                HGTRY(sync_watchful());
                 if (host.done) break;
             }
             if (fuse && host.iter > iter0 && host.done != 2) {
@@ -1552,7 +1632,7 @@ struct Solver : SolverBase {
             if (host.done == 2) break;
         }
         CU(cudaEventRecord(ev1, stream));
-        CU(cudaStreamSynchronize(stream));
+        HGTRY(sync_watchful());
         CU(cudaGetLastError());
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, ev0, ev1));
@@ -1758,6 +1838,8 @@ int hg_comm_init(hg_handle h, const uint8_t* id, int rank, int world, int ghost_
     return h->impl->comm_init(id, rank, world, ghost_top, ghost_bottom, row_starts, global_rows);
 }
 int hg_reset_guess(hg_handle h) { CHECK_H(h); return h->impl->reset_guess(); }
+int hg_set_phase_timing(hg_handle h, int enable) { CHECK_H(h); return h->impl->set_phase_timing(enable); }
+int hg_get_phase_ms(hg_handle h, double* ms, int* counts, int n) { CHECK_H(h); return h->impl->get_phase_ms(ms, counts, n); }
 int hg_mg_levels(hg_handle h) { CHECK_H(h); return h->impl->mg_levels(); }
 int hg_mg_get_level(hg_handle h, int level, int* rows, int* cols, double* coef9) { CHECK_H(h); return h->impl->mg_get_level(level, rows, cols, coef9); }
 

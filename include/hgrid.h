@@ -59,7 +59,8 @@ typedef enum {
     HG_ERR_EMPTY_ROWS = -5,    /* bilaplacian without cuts: wrong number of empty rows (:493)       */
     HG_ERR_NOT_CONVERGED = -6, /* maxiter reached (the reference asserts info == 0, recovery.py:972) */
     HG_ERR_BREAKDOWN = -7,     /* NaN / non-positive curvature: singular or under-constrained system */
-    HG_ERR_NOMEM = -8
+    HG_ERR_NOMEM = -8,
+    HG_ERR_COMM = -9           /* slab mode: NCCL failure or a peer that stopped; the communicator is aborted */
 } hg_status;
 
 typedef struct {
@@ -176,6 +177,26 @@ int hg_mg_get_level(hg_handle h, int level, int* rows, int* cols, double* coef9)
 /* Times `iters` launches of the stencil kernel on device-resident data (CUDA events on
  * the solver's stream); returns mean milliseconds per launch. */
 int hg_bench_apply(hg_handle h, int iters, double* ms_per_launch);
+
+/* Per-phase device time of the MG-PCG loop (Laplacian + multigrid path): after hg_set_phase_timing(h, 1) every
+ * hg_solve_device records CUDA events on the solver's stream between its launches; hg_get_phase_ms returns, per
+ * phase, the milliseconds (and the number of intervals) of the last solve.  The events cost a few microseconds
+ * each, so a timed benchmark run leaves this off.  No reference counterpart (tictoc.py prints host wall time). */
+enum {
+    HG_PH_OTHER = 0,
+    HG_PH_STENCIL = 1,   /* q = A p, p.q, alpha                                  */
+    HG_PH_UPDATE = 2,    /* x += alpha p, r -= alpha q, r.r, convergence check   */
+    HG_PH_FINE_DOWN = 3, /* V-cycle level 0, downward leg (+ ghost exchange of r) */
+    HG_PH_L1_DOWN = 4,   /* level 1, downward leg                                 */
+    HG_PH_COARSE = 5,    /* levels >= 2, both legs, coarsest solve                */
+    HG_PH_L1_UP = 6,     /* level 1, upward leg                                   */
+    HG_PH_FINE_UP = 7,   /* level 0, upward leg, r.z                              */
+    HG_PH_PUPDATE = 8,   /* beta, p = z + beta p                                  */
+    HG_PH_OUTER = 9,     /* true residual in fp64 (outer refinement loop)         */
+    HG_N_PHASES = 10
+};
+int hg_set_phase_timing(hg_handle h, int enable);
+int hg_get_phase_ms(hg_handle h, double* ms, int* counts, int n);
 
 #ifdef __cplusplus
 }

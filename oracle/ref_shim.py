@@ -6,8 +6,9 @@ Import shim that lets the UNMODIFIED reference (`/root/reference/recovery.py`,
 numpy restatement in `oracle/grid_oracle.py` and (b) generate the golden vectors
 committed under `tests/golden/` (see `oracle/make_golden.py`).
 
-`/root/reference` does not exist on the GPU box, so nothing that runs there may
-import this file; `have_reference()` says whether it is usable.
+`/root/reference` does not exist on the GPU box; there the verbatim copy under
+oracle/_ref/ (oracle/build_ref.py) is used by bench.py's CPU legs only.
+`have_reference()` says whether either is present.
 
 Why a shim is needed:
   * `tictoc.py:9,12` calls `time.clock`, removed in Python 3.8.
@@ -24,7 +25,11 @@ import types
 
 import numpy as np
 
-REFERENCE_DIR = os.environ.get("HGRID_REFERENCE_DIR", "/root/reference")
+# the reference tree where it lies (build container), else the verbatim copy made by oracle/build_ref.py
+# (oracle/_ref/, git-ignored, travels to the GPU box)
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REFERENCE_DIR = os.environ.get("HGRID_REFERENCE_DIR") or (
+    "/root/reference" if os.path.isfile("/root/reference/recovery.py") else os.path.join(_HERE, "_ref"))
 
 
 def have_reference():
