@@ -63,6 +63,7 @@ SYMBOLS = {
     "hg_comm_unique_id": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint8)]),
     "hg_comm_init": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                     ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    "hg_mg_get_level_vectors": (ctypes.c_int, [_H, ctypes.c_int, _dp, _dp]),
     "hg_set_phase_timing": (ctypes.c_int, [_H, ctypes.c_int]),
     "hg_get_phase_ms": (ctypes.c_int, [_H, _dp, ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
     "hg_bench_apply": (ctypes.c_int, [_H, ctypes.c_int, _dp]),

@@ -378,7 +378,8 @@ cup_kernel(Coarse<T> L, Coarse<T> Lc, const int* __restrict__ done) {
     __syncthreads();
     cf_sweep<T, KC, true, CF_ALL8, false>(L, S, 0, gi0, gj0, k0, kn, L.b);
     __syncthreads();
-    cf_store_tile(L, S, ti0, tj0, k0, kn, L.x);
+    // (to the second buffer: neighbouring tiles read this tile's pre-smoothed x as their halo)
+    cf_store_tile(L, S, ti0, tj0, k0, kn, L.x2);
 }
 
 }  // namespace hg

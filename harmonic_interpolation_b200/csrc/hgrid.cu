@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "coarse_fused.cuh"
+#include "coarse_stream.cuh"
 #include "common.cuh"
 #include "fine.cuh"
 #include "fine_stream.cuh"
@@ -131,6 +132,7 @@ struct SolverBase {
     virtual int upload_u8(const uint8_t* vals, hg_stats* st) = 0;
     virtual int download_u8(uint8_t* out, hg_stats* st) = 0;
     virtual int comm_init(const uint8_t* id, int rank, int world, int ghost_top, int ghost_bottom, const int* row_starts, int global_rows) = 0;
+    virtual int mg_get_level_vectors(int level, double* x, double* b) = 0;
     virtual int set_phase_timing(int on) = 0;
     virtual int get_phase_ms(double* ms, int* counts, int n) = 0;
 };
@@ -424,7 +426,7 @@ struct Solver : SolverBase {
     // ---- multigrid ----------------------------------------------------------------------------
     void free_hierarchy() {
         for (auto* lv : {&coarse, &gcoarse}) {
-            for (auto& c : *lv) { cudaFree(c.coef); cudaFree(c.x); cudaFree(c.b); cudaFree(c.code); cudaFree(c.act_up); cudaFree(c.act_down); }
+            for (auto& c : *lv) { cudaFree(c.coef); cudaFree(c.x); cudaFree(c.x2); cudaFree(c.b); cudaFree(c.code); cudaFree(c.act_up); cudaFree(c.act_down); cudaFree(c.cs_act); }
             lv->clear();
         }
         cudaFree(d_dense); cudaFree(d_gdense);
@@ -447,8 +449,9 @@ struct Solver : SolverBase {
         L.pitch = round_up(c, 32);
         L.plane = (long long)L.rows * L.pitch;
         L.K = K;
-        L.coef = L.x = L.b = nullptr;
+        L.coef = L.x = L.b = L.x2 = nullptr;
         L.code = L.act_up = L.act_down = nullptr;
+        L.cs_act = nullptr; L.cs_cr = L.cs_ns = L.cs_nt = 0;
         L.tiles_x = (L.pitch + CF_TX - 1) / CF_TX;
         L.tiles_y = (L.rows + CF_TY - 1) / CF_TY;
         L.has_ref = 0;
@@ -459,6 +462,8 @@ struct Solver : SolverBase {
         CU(cudaMalloc(&L.coef, (size_t)L.plane * 9 * sizeof(T)));
         CU(cudaMalloc(&L.x, (size_t)L.plane * K * sizeof(T)));
         CU(cudaMalloc(&L.b, (size_t)L.plane * K * sizeof(T)));
+        CU(cudaMalloc(&L.x2, (size_t)L.plane * K * sizeof(T)));
+        CU(cudaMemsetAsync(L.x2, 0, (size_t)L.plane * K * sizeof(T), stream));
         CU(cudaMemsetAsync(L.coef, 0, (size_t)L.plane * 9 * sizeof(T), stream));
         CU(cudaMemsetAsync(L.x, 0, (size_t)L.plane * K * sizeof(T), stream));
         CU(cudaMemsetAsync(L.b, 0, (size_t)L.plane * K * sizeof(T), stream));
@@ -514,13 +519,35 @@ struct Solver : SolverBase {
         ccode_kernel<T><<<dim3((L.pitch + 255) / 256, L.rows), 256, 0, stream>>>(L);
         ctile_activity_kernel<<<dim3(L.tiles_x, L.tiles_y), 256, 0, stream>>>(L.code, L.rows, L.cols, L.pitch, 0, L.act_up);
         ctile_activity_kernel<<<dim3(L.tiles_x, L.tiles_y), 256, 0, stream>>>(L.code, L.rows, L.cols, L.pitch, 1, L.act_down);
+        // streaming legs (coarse_stream.cuh) on every level that is large enough to feed warps with 120-column strips;
+        // chunks of 64 rows where that still gives every SM several blocks, 16 rows on the smaller levels
+        L.cs_cr = 0;
+        if (!coarse_tiles && (long long)L.rows * L.cols > 256 && L.plane < (1LL << 31)) {
+            L.cs_ns = (L.pitch + CS_OUT - 1) / CS_OUT;
+            const long long warps64 = (long long)L.cs_ns * ((L.rows + 63) / 64) * K;
+            L.cs_cr = warps64 >= 148LL * 8 * 2 ? 64 : 16;
+            L.cs_nt = (L.rows + L.cs_cr - 1) / L.cs_cr;
+            CU(cudaMalloc(&L.cs_act, (size_t)L.cs_ns * L.cs_nt));
+            cs_activity_kernel<<<dim3(L.cs_ns, L.cs_nt), 256, 0, stream>>>(L.code, L.rows, L.cols, L.pitch, L.cs_cr, L.cs_ns, L.cs_act);
+        }
         return HG_OK;
+    }
+    bool coarse_tiles = getenv("HGRID_COARSE_TILES") != nullptr;     // A/B aid: the shared-memory tile legs of coarse_fused.cuh on every level
+    template <bool UP>
+    void launch_cs(const Coarse<T>& L, const Coarse<T>& Lc, const int* done) {
+        constexpr int WPB = CsCfg<T>::WPB;
+        const int nchunks = L.cs_ns * L.cs_nt;
+        const unsigned blocks = (unsigned)(((long long)nchunks * K + WPB - 1) / WPB);
+        const size_t sm = (size_t)(UP ? 2 : 1) * WPB * CS_RING * 128 * sizeof(T);
+        cs_leg_kernel<T, UP><<<blocks, 32 * WPB, sm, stream>>>(L, Lc, 1, L.cs_act, L.cs_cr, L.cs_ns, nchunks, done);
     }
 
     template <int KC>
     int set_fused_attrs() {
         CU(cudaFuncSetAttribute(cdown_kernel<T, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CFSmem<T, KC, false>)));
         CU(cudaFuncSetAttribute(cup_kernel<T, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CFSmem<T, KC, true>)));
+        CU(cudaFuncSetAttribute(cs_leg_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * CsCfg<T>::WPB * CS_RING * 128 * sizeof(T))));
+        CU(cudaFuncSetAttribute(cs_leg_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CsCfg<T>::WPB * CS_RING * 128 * sizeof(T))));
         return HG_OK;
     }
     template <int KC>
@@ -534,6 +561,7 @@ struct Solver : SolverBase {
     // fused legs of a 9-point level: pre-smoothing + residual + restriction / prolongation + post-smoothing
     void coarse_down(const Coarse<T>& L, const Coarse<T>& Lc, const int* done) {
         if (unfused_coarse) { coarse_pre(L, done); coarse_restrict(L, Lc, done); return; }
+        if (L.cs_cr) { launch_cs<false>(L, Lc, done); ++launches; return; }
         switch (std::min(K, 4)) {
             case 1: launch_cdown<1>(L, Lc, done); break;
             case 2: launch_cdown<2>(L, Lc, done); break;
@@ -542,14 +570,18 @@ struct Solver : SolverBase {
         }
         ++launches;
     }
-    void coarse_up(const Coarse<T>& L, const Coarse<T>& Lc, const int* done) {
+    // (the fused upward legs write x2; afterwards x2 IS the level's x: the host-side structs are swapped, every later
+    // launch -- the level above, the next V-cycle -- takes the struct by value and sees the current pointers)
+    void coarse_up(Coarse<T>& L, const Coarse<T>& Lc, const int* done) {
         if (unfused_coarse) { coarse_prolong(L, Lc, done); coarse_post(L, done); return; }
-        switch (std::min(K, 4)) {
+        if (L.cs_cr) launch_cs<true>(L, Lc, done);
+        else switch (std::min(K, 4)) {
             case 1: launch_cup<1>(L, Lc, done); break;
             case 2: launch_cup<2>(L, Lc, done); break;
             case 3: launch_cup<3>(L, Lc, done); break;
             default: launch_cup<4>(L, Lc, done); break;
         }
+        std::swap(L.x, L.x2);
         ++launches;
     }
 
@@ -918,7 +950,7 @@ struct Solver : SolverBase {
         ++launches;
     }
     // V-cycle over levels[from..] of a hierarchy whose first level already holds b (and x = 0)
-    void coarse_vcycle(const std::vector<Coarse<T>>& lv, const double* dense, const int* done) {
+    void coarse_vcycle(std::vector<Coarse<T>>& lv, const double* dense, const int* done) {
         const int n = (int)lv.size();
         const bool top = &lv == &coarse;      // (marks: level 1 of the local hierarchy on its own)
         for (int l = 0; l + 1 < n; ++l) {
@@ -1151,6 +1183,24 @@ struct Solver : SolverBase {
                 for (int i = 0; i < L.rows; ++i)
                     for (int j = 0; j < L.cols; ++j)
                         coef9[((size_t)i * L.cols + j) * 9 + c] = (double)tmp[(size_t)c * L.plane + (size_t)i * L.pitch + j];
+        }
+        return HG_OK;
+    }
+
+    // x and b of hierarchy level >= 1 as the last V-cycle left them, (rows, cols, K) float64 (debugging / tests of the legs)
+    int mg_get_level_vectors(int level, double* xo, double* bo) override {
+        if (level < 1 || level > (int)coarse.size()) return fail(HG_ERR_INVALID, "hg_mg_get_level_vectors: no such level");
+        const Coarse<T>& L = coarse[level - 1];
+        std::vector<T> tmp((size_t)L.plane * K);
+        for (int which = 0; which < 2; ++which) {
+            double* out = which ? bo : xo;
+            if (!out) continue;
+            CU(cudaMemcpyAsync(tmp.data(), which ? L.b : L.x, tmp.size() * sizeof(T), cudaMemcpyDeviceToHost, stream));
+            CU(cudaStreamSynchronize(stream));
+            for (int k = 0; k < K; ++k)
+                for (int i = 0; i < L.rows; ++i)
+                    for (int j = 0; j < L.cols; ++j)
+                        out[((size_t)i * L.cols + j) * K + k] = (double)tmp[(size_t)k * L.plane + (size_t)i * L.pitch + j];
         }
         return HG_OK;
     }
@@ -1838,6 +1888,7 @@ int hg_comm_init(hg_handle h, const uint8_t* id, int rank, int world, int ghost_
     return h->impl->comm_init(id, rank, world, ghost_top, ghost_bottom, row_starts, global_rows);
 }
 int hg_reset_guess(hg_handle h) { CHECK_H(h); return h->impl->reset_guess(); }
+int hg_mg_get_level_vectors(hg_handle h, int level, double* x, double* b) { CHECK_H(h); return h->impl->mg_get_level_vectors(level, x, b); }
 int hg_set_phase_timing(hg_handle h, int enable) { CHECK_H(h); return h->impl->set_phase_timing(enable); }
 int hg_get_phase_ms(hg_handle h, double* ms, int* counts, int n) { CHECK_H(h); return h->impl->get_phase_ms(ms, counts, n); }
 int hg_mg_levels(hg_handle h) { CHECK_H(h); return h->impl->mg_levels(); }

@@ -29,6 +29,8 @@ struct Coarse {
     T* coef;   // 9 planes
     T* x;      // K planes
     T* b;      // K planes
+    T* x2;     // K planes: the fused upward legs write here (x + P e and the post-smoothing read x of NEIGHBOURING tiles /
+               // chunks, which must still hold the pre-smoothed values); the host swaps x and x2 after the launch
     // fused legs (coarse_fused.cuh): code byte per pixel (0 inactive, 1 regular = coefficients equal
     // `ref`, 2 general), activity of the 64 x 32 tiles (halo 0 / halo 1), the level's interior stencil
     uint8_t* code;
@@ -37,6 +39,9 @@ struct Coarse {
     int tiles_x, tiles_y;
     int has_ref;
     T ref[9];
+    // streaming legs (coarse_stream.cuh): chunks of 120 columns x cs_cr rows, activity bits per chunk; cs_cr == 0: tile legs
+    uint8_t* cs_act;
+    int cs_cr, cs_ns, cs_nt;
 };
 
 // ---- transfer weights ---------------------------------------------------------------------

@@ -211,6 +211,14 @@ class GridSolver:
         C.check(self._lib.hg_mg_get_level(self._h, level, ctypes.byref(r), ctypes.byref(c), C.dptr(out)))
         return out
 
+    def mg_level_vectors(self, level):
+        """(x, b) of hierarchy level >= 1 as the last V-cycle left them, each (rows, cols, K) float64."""
+        r, c = ctypes.c_int(), ctypes.c_int()
+        C.check(self._lib.hg_mg_get_level(self._h, level, ctypes.byref(r), ctypes.byref(c), C.dptr(None)))
+        x = np.empty((r.value, c.value, self.K)); b = np.empty((r.value, c.value, self.K))
+        C.check(self._lib.hg_mg_get_level_vectors(self._h, level, C.dptr(x), C.dptr(b)))
+        return x, b
+
     def bench_apply(self, iters=20):
         ms = ctypes.c_double()
         C.check(self._lib.hg_bench_apply(self._h, int(iters), ctypes.byref(ms)))

@@ -174,6 +174,10 @@ int hg_precond_apply(hg_handle h, const double* r, double* z);
 int hg_mg_levels(hg_handle h);
 int hg_mg_get_level(hg_handle h, int level, int* rows, int* cols, double* coef9);
 
+/* x and b of hierarchy level >= 1 as the last V-cycle left them, each (rows, cols, K) float64 or NULL: lets a test compare
+ * the legs of the V-cycle level by level (tile legs / streaming legs / the unfused reference kernels). */
+int hg_mg_get_level_vectors(hg_handle h, int level, double* x, double* b);
+
 /* Times `iters` launches of the stencil kernel on device-resident data (CUDA events on
  * the solver's stream); returns mean milliseconds per launch. */
 int hg_bench_apply(hg_handle h, int iters, double* ms_per_launch);

@@ -293,3 +293,40 @@ def test_fused_cg_loop_matches_the_separate_kernels(monkeypatch):
         b, ib = res[(True, prec)]
         assert abs(ia - ib) <= 1, (prec, ia, ib)
         assert np.abs(a - b).max() < tol
+
+
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+@pytest.mark.parametrize("shape", [(700, 900), (2050, 1030), (130, 4100), (97, 61)])
+def test_streaming_coarse_legs_match_tile_legs(monkeypatch, prec, shape):
+    """The register-pipeline legs of the 9-point levels (coarse_stream.cuh) compute the same V-cycle as the shared-memory
+    tile legs (coarse_fused.cuh, HGRID_COARSE_TILES=1): regular and general pixels, inactive areas, cuts, soft weights,
+    ragged sizes, K = 3."""
+    rows, cols = shape
+    rng = np.random.default_rng(rows * 7 + cols)
+    p = problem(rng, rows, cols, K=3, cuts=False, hard_p=0.0)
+    h = cols // 2
+    # left half: 64-pixel tiles (large regular areas, straight edges, a few soft pixels); right half: scattered hard pixels
+    # and cut cells (general pixels everywhere)
+    tiles = np.kron(rng.random((rows // 64 + 1, cols // 64 + 1)) < 0.5, np.ones((64, 64), bool))[:rows, :cols]
+    p.hard[:, :h] |= tiles[:, :h]
+    p.hard[:, h:] |= rng.random((rows, cols - h)) < 0.03
+    block = np.kron(rng.random((rows // 8 + 1, cols // 8 + 1)) < 0.3, np.ones((8, 8), bool))[:rows, :cols]
+    cd, cr = R.cut_planes_from_mask(block)
+    cd[:, :h] = False; cr[:, :h] = False
+    p.cut_down, p.cut_right = cd, cr
+    p.hard[0::8, h - (h % 8)::8] = True
+    p.soft_w[:, :h] *= rng.random((rows, h)) < 0.02
+    p.soft_w[p.hard] = 0.0
+    a = rng.normal(size=(rows, cols, 3))
+    a[p.hard] = 0
+    monkeypatch.setenv("HGRID_COARSE_TILES", "1")
+    s0 = solver_for(p, prec)
+    z0 = s0.precond_apply(a)
+    s0.close()
+    monkeypatch.delenv("HGRID_COARSE_TILES")
+    s1 = solver_for(p, prec)
+    z1 = s1.precond_apply(a)
+    s1.close()
+    assert np.isfinite(z1).all()
+    scale = np.abs(z0).max()
+    assert np.abs(z1 - z0).max() <= (1e-11 if prec == "fp64" else 5e-5) * scale, np.abs(z1 - z0).max() / scale
