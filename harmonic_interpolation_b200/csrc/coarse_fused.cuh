@@ -71,12 +71,12 @@ __global__ void ccode_kernel(Coarse<T> L) {
     if (j >= L.pitch) return;
     const long long o = (long long)i * L.pitch + j;
     unsigned c = 0;
-    if (j < L.cols && L.coef[4 * L.plane + o] != T(0)) {
+    if (j < L.cols && L.coef[cidx(4, o)] != T(0)) {
         c = 2;
         if (L.has_ref) {
             bool same = true;
 #pragma unroll
-            for (int n = 0; n < 9; ++n) same = same && (L.coef[n * L.plane + o] == L.ref[n]);
+            for (int n = 0; n < 9; ++n) same = same && (L.coef[cidx(n, o)] == L.ref[n]);
             if (same) c = 1;
         }
     }
@@ -141,7 +141,7 @@ __device__ __forceinline__ void cf_coefs(const Coarse<T>& L, unsigned code, long
         for (int n = 0; n < 9; ++n) cf[n] = L.ref[n];
     } else {
 #pragma unroll
-        for (int n = 0; n < 9; ++n) cf[n] = ((MASK >> n) & 1) ? L.coef[n * L.plane + o] : T(0);
+        for (int n = 0; n < 9; ++n) cf[n] = ((MASK >> n) & 1) ? L.coef[cidx(n, o)] : T(0);
     }
 }
 

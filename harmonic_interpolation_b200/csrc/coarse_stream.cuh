@@ -39,8 +39,33 @@ namespace hg {
 #define CS_OUT 120
 #define CS_RING 8                       // rows of the shared-memory FIFO (row <-> slot row & 7)
 // warps per block: the pipeline state of a warp is ~165 registers (fp32), so one block per SM: 12 warps (fp32) / 8 (fp64)
-template <typename T> struct CsCfg { static constexpr int WPB = sizeof(T) == 4 ? 12 : 8; };
-__device__ __forceinline__ void cs_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+template <typename T, bool UP> struct CsCfg { static constexpr int WPB = sizeof(T) == 4 ? 12 : 8; };
+// Brings a line into L1 without a register destination (a load into a dummy register makes the next writer of that
+// register wait for HBM; prefetch.global.L1 gave no measurable hit rate): a 4-byte cp.async.ca into a scratch word.
+__device__ __forceinline__ void cs_touch(const void* gmem, void* scratch) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(scratch);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem) : "memory");
+}
+// 1 / x: fp32 by the approximate reciprocal and one Newton step (no slow path, no branch); fp64 by division
+__device__ __forceinline__ float cs_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r * (2.0f - x * r);
+}
+__device__ __forceinline__ double cs_rcp(double x) { return 1.0 / x; }
+__device__ __forceinline__ V4<float> ldg4(const float* p) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    V4<float> r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
+}
+__device__ __forceinline__ V4<double> ldg4(const double* p) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p + 2));
+    V4<double> r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; return r;
+}
+// the broadcast copy of a level's interior stencil: refq[n * 4 + p] = ref[n]
+template <typename T>
+__global__ void cs_refq_kernel(Coarse<T> L) {
+    if (threadIdx.x < 36) L.refq[threadIdx.x] = L.ref[threadIdx.x >> 2];
+}
 
 // activity of the chunks of a level: bit 0 any active pixel in the chunk, bit 1 any within the chunk grown by one pixel
 __global__ void cs_activity_kernel(const uint8_t* __restrict__ code, int rows, int cols, int pitch, int cr, int ns, uint8_t* __restrict__ act) {
@@ -87,6 +112,7 @@ struct CsWarp {
     const T* pb;                    // up: b
     T* xk;                          // x (stored)
     T* ringA; T* ringB;             // this lane's quad in slot 0 of the warp's rings
+    float* scratch;                 // this lane's scratch word (target of the L1 touches)
     // next-coarser level
     const uint8_t* ccode;
     T* cb;                          // down: b_{l+1} of this channel
@@ -100,6 +126,11 @@ struct CsWarp {
     T L3u[12], R0u[12];             // up: the same after the row's sweep
     T EA[4][3];                     // up: next-coarser rows (slot I & 3): the lane's two columns and the next lane's first
 
+    unsigned ccnext;
+    __device__ __forceinline__ unsigned load_ccode(int I) const {
+        const int Ja = c0 >> 1;
+        return (colin && owner && (unsigned)I < (unsigned)crows && Ja < ccols) ? *reinterpret_cast<const unsigned short*>(ccode + ((long long)I * cpitch + Ja)) : 0u;
+    }
     __device__ __forceinline__ unsigned load_code(int rho) const {
         const int r = rbase + rho;
         return (colin && (unsigned)r < (unsigned)rows) ? *reinterpret_cast<const unsigned*>(code + ((long long)r * pitch + c0)) : 0u;
@@ -123,89 +154,103 @@ struct CsWarp {
         }
         sl_cp_commit();
     }
-    // the coefficient sectors of a quad with a general pixel -> L1, one step before the colour steps need them (the loads
-    // inside a colour step sit on the dependent chain of the sweep: an L2 / HBM round trip there stalls the warp)
+    // the coefficients of a quad with a general pixel (144 contiguous bytes, two lines) -> L1 one step before they are
+    // needed: the loads inside a step sit on the dependent chain of the sweep, an L2 / HBM round trip there stalls the warp
     __device__ __forceinline__ void prefetch_coefs(int rho, unsigned cw) const {
         if (cw & 0x02020202u) {
-            const T* base = coef + ((long long)(rbase + rho) * pitch + c0);
-#pragma unroll
-            for (int n = 0; n < 9; ++n) cs_prefetch_l1(base + n * plane);
+            const T* base = coef + (((long long)(rbase + rho) * pitch + c0) >> 2) * 36;
+            cs_touch(base, scratch);
+            cs_touch(base + 32, scratch);
         }
     }
     __device__ __forceinline__ V4<T> rowA(int rho) const { return ld4(ringA + (rho & (CS_RING - 1)) * 128); }
     __device__ __forceinline__ V4<T> rowB(int rho) const { return ld4(ringB + (rho & (CS_RING - 1)) * 128); }
 
-    // nine coefficients of pixel p of relative row rho: the register stencil, or (GEN, code 2) the planes -- only MASK (+ centre)
-    template <int MASK, bool GEN>
-    __device__ __forceinline__ void coefs(unsigned cw, int rho, int p, T (&cf)[9], T& inv) const {
+    // ---- coefficients of a row ------------------------------------------------------------------------------------
+    // CfRef: the level's interior stencil, from registers (no lane of the warp holds a general pixel in this row).
+    // CfQuad: the quad's nine coefficient vectors from memory -- EVERY active pixel's coefficients are stored, regular ones
+    // included, so no per-pixel choice is needed; a lane whose quad holds no general pixel reads the level's broadcast
+    // copy of the interior stencil instead (`refq`, same [9][4] layout, always in L1): only general quads cost HBM traffic.
+    struct CfRef {
+        const T* r; T inv;
+        template <int N, int P> __device__ __forceinline__ T get() const { return r[N]; }
+        template <int P> __device__ __forceinline__ T invc() const { return inv; }
+    };
+    struct CfQuad {
+        V4<T> v[9];
+        template <int N, int P> __device__ __forceinline__ T get() const { return v[N].v[P]; }
+        template <int P> __device__ __forceinline__ T invc() const { return cs_rcp(v[4].v[P]); }
+    };
+    const T* refq;
+    template <int SET>
+    __device__ __forceinline__ void load_quads(CfQuad& q, int rho, unsigned cw) const {
+        const bool gen = (cw & 0x02020202u) != 0u;
+        const T* base = gen ? coef + (((long long)(rbase + rho) * pitch + c0) >> 2) * 36 : refq;
 #pragma unroll
-        for (int n = 0; n < 9; ++n) cf[n] = ref[n];
-        inv = inv_ref;
-        if (GEN) {
-            if (((cw >> (8 * p)) & 0xffu) == 2u) {
-                const T* base = coef + ((long long)(rbase + rho) * pitch + c0 + p);
-#pragma unroll
-                for (int n = 0; n < 9; ++n)
-                    if ((MASK >> n) & 1) cf[n] = __ldg(base + n * plane);
-                if (MASK & 0x010) inv = T(1) / cf[4];
-            }
-        }
+        for (int n = 0; n < 9; ++n)
+            if ((SET >> n) & 1) q.v[n] = ldg4(base + 4 * n);
     }
-    // sum over the neighbours in MASK of coefficient * value; U / M / D: rows above / own / below with their lane-edge values
-    template <int MASK, int P>
-    __device__ __forceinline__ static T nsum(const T (&cf)[9], const V4<T>& U, T ul, T ur, const V4<T>& M, T ml, T mr, const V4<T>& D, T dl, T dr) {
+    // sum over the neighbours in MASK of coefficient * value for pixel P; U / M / D: rows above / own / below with their lane-edge values
+    template <int MASK, int P, typename CF>
+    __device__ __forceinline__ static T nsum(const CF& cf, const V4<T>& U, T ul, T ur, const V4<T>& M, T ml, T mr, const V4<T>& D, T dl, T dr) {
         T s = T(0);
-        if (MASK & 0x008) s += cf[3] * cs_at<P - 1>(M, ml, mr);
-        if (MASK & 0x020) s += cf[5] * cs_at<P + 1>(M, ml, mr);
-        if (MASK & 0x002) s += cf[1] * cs_at<P>(U, ul, ur);
-        if (MASK & 0x080) s += cf[7] * cs_at<P>(D, dl, dr);
-        if (MASK & 0x001) s += cf[0] * cs_at<P - 1>(U, ul, ur);
-        if (MASK & 0x004) s += cf[2] * cs_at<P + 1>(U, ul, ur);
-        if (MASK & 0x040) s += cf[6] * cs_at<P - 1>(D, dl, dr);
-        if (MASK & 0x100) s += cf[8] * cs_at<P + 1>(D, dl, dr);
+        if (MASK & 0x008) s += cf.template get<3, P>() * cs_at<P - 1>(M, ml, mr);
+        if (MASK & 0x020) s += cf.template get<5, P>() * cs_at<P + 1>(M, ml, mr);
+        if (MASK & 0x002) s += cf.template get<1, P>() * cs_at<P>(U, ul, ur);
+        if (MASK & 0x080) s += cf.template get<7, P>() * cs_at<P>(D, dl, dr);
+        if (MASK & 0x001) s += cf.template get<0, P>() * cs_at<P - 1>(U, ul, ur);
+        if (MASK & 0x004) s += cf.template get<2, P>() * cs_at<P + 1>(U, ul, ur);
+        if (MASK & 0x040) s += cf.template get<6, P>() * cs_at<P - 1>(D, dl, dr);
+        if (MASK & 0x100) s += cf.template get<8, P>() * cs_at<P + 1>(D, dl, dr);
         return s;
     }
-    // Gauss-Seidel update of pixels PAR, PAR + 2 of the row in slot SM (rows above / below in SU / SD), right-hand side rhs
-    template <int MASK, int PAR, bool GEN>
-    __device__ __forceinline__ void update2(int rho, unsigned cw, V4<T>& M, const V4<T>& rhs, const V4<T>& U, T ul, T ur, T ml, T mr,
-                                            const V4<T>& D, T dl, T dr) const {
-        T cfa[9], cfb[9], ia, ib;
-        coefs<MASK | 0x010, GEN>(cw, rho, PAR, cfa, ia);
-        coefs<MASK | 0x010, GEN>(cw, rho, PAR + 2, cfb, ib);
-        const T sa = nsum<MASK, PAR>(cfa, U, ul, ur, M, ml, mr, D, dl, dr);
-        const T sb = nsum<MASK, PAR + 2>(cfb, U, ul, ur, M, ml, mr, D, dl, dr);
-        M.v[PAR] = (cw & (0xffu << (8 * PAR))) ? (rhs.v[PAR] - sa) * ia : T(0);
-        M.v[PAR + 2] = (cw & (0xffu << (8 * (PAR + 2)))) ? (rhs.v[PAR + 2] - sb) * ib : T(0);
-    }
-    template <int MASK, int PAR>
-    __device__ __forceinline__ void update(int rho, unsigned cw, V4<T>& M, const V4<T>& rhs, const V4<T>& U, T ul, T ur, T ml, T mr,
-                                           const V4<T>& D, T dl, T dr) const {
-        const unsigned gen = cw & ((0x02u << (8 * PAR)) | (0x02u << (8 * (PAR + 2))));
-        if (__any_sync(HG_FULL, gen != 0u)) update2<MASK, PAR, true>(rho, cw, M, rhs, U, ul, ur, ml, mr, D, dl, dr);
-        else update2<MASK, PAR, false>(rho, cw, M, rhs, U, ul, ur, ml, mr, D, dl, dr);
+    // Gauss-Seidel update of pixels PAR, PAR + 2 of the row M (code word cw), right-hand side rhs
+    template <int MASK, int PAR, typename CF>
+    __device__ __forceinline__ static void update(const CF& cf, unsigned cw, V4<T>& M, const V4<T>& rhs, const V4<T>& U, T ul, T ur, T ml, T mr,
+                                                  const V4<T>& D, T dl, T dr) {
+        const T sa = nsum<MASK, PAR>(cf, U, ul, ur, M, ml, mr, D, dl, dr);
+        const T sb = nsum<MASK, PAR + 2>(cf, U, ul, ur, M, ml, mr, D, dl, dr);
+        M.v[PAR] = (cw & (0xffu << (8 * PAR))) ? (rhs.v[PAR] - sa) * cf.template invc<PAR>() : T(0);
+        M.v[PAR + 2] = (cw & (0xffu << (8 * (PAR + 2)))) ? (rhs.v[PAR + 2] - sb) * cf.template invc<PAR + 2>() : T(0);
     }
     // residual (minus the couplings in MASK) of pixels PAR, PAR + 2 of the row M into Rm
-    template <int MASK, int PAR, bool GEN>
-    __device__ __forceinline__ void resid2(int rho, unsigned cw, V4<T>& Rm, const V4<T>& U, T ul, T ur, const V4<T>& M, T ml, T mr,
-                                           const V4<T>& D, T dl, T dr) const {
-        T cfa[9], cfb[9], ia, ib;
-        coefs<MASK & ~0x010, GEN>(cw, rho, PAR, cfa, ia);
-        coefs<MASK & ~0x010, GEN>(cw, rho, PAR + 2, cfb, ib);
-        const T sa = nsum<MASK, PAR>(cfa, U, ul, ur, M, ml, mr, D, dl, dr);
-        const T sb = nsum<MASK, PAR + 2>(cfb, U, ul, ur, M, ml, mr, D, dl, dr);
+    template <int MASK, int PAR, typename CF>
+    __device__ __forceinline__ static void resid(const CF& cf, unsigned cw, V4<T>& Rm, const V4<T>& U, T ul, T ur, const V4<T>& M, T ml, T mr,
+                                                 const V4<T>& D, T dl, T dr) {
+        const T sa = nsum<MASK, PAR>(cf, U, ul, ur, M, ml, mr, D, dl, dr);
+        const T sb = nsum<MASK, PAR + 2>(cf, U, ul, ur, M, ml, mr, D, dl, dr);
         Rm.v[PAR] = (cw & (0xffu << (8 * PAR))) ? -sa : T(0);
         Rm.v[PAR + 2] = (cw & (0xffu << (8 * (PAR + 2)))) ? -sb : T(0);
     }
-    template <int MASK, int PAR>
-    __device__ __forceinline__ void resid(int rho, unsigned cw, V4<T>& Rm, const V4<T>& U, T ul, T ur, const V4<T>& M, T ml, T mr,
-                                          const V4<T>& D, T dl, T dr) const {
-        const unsigned gen = cw & ((0x02u << (8 * PAR)) | (0x02u << (8 * (PAR + 2))));
-        if (__any_sync(HG_FULL, gen != 0u)) resid2<MASK, PAR, true>(rho, cw, Rm, U, ul, ur, M, ml, mr, D, dl, dr);
-        else resid2<MASK, PAR, false>(rho, cw, Rm, U, ul, ur, M, ml, mr, D, dl, dr);
-    }
+    __device__ __forceinline__ bool any_general(unsigned cw) const { return __any_sync(HG_FULL, (cw & 0x02020202u) != 0u) != 0; }
     __device__ __forceinline__ bool own_row(int r) const { return r >= i0 && r < i0 + cr && r < rows && owner && colin; }
 
     // ---- downward leg ---------------------------------------------------------------------------------
+    template <int SE, typename CF> __device__ __forceinline__ void down_even(const CF& cf, const V4<T>& bE) {
+        const T zero = T(0);
+        const V4<T> none = zero4<T>();
+        X[SE] = zero4<T>();
+        update<0, 0>(cf, C[SE], X[SE], bE, none, zero, zero, zero, zero, none, zero, zero);
+        R0[SE] = sl_dn1(X[SE].v[0]);
+        update<CF_ROW, 1>(cf, C[SE], X[SE], bE, none, zero, zero, zero, R0[SE], none, zero, zero);
+        L3[SE] = sl_up1(X[SE].v[3]);
+    }
+    template <int SO, int SP, int SE, typename CF> __device__ __forceinline__ void down_odd(const CF& cf, const V4<T>& bO) {
+        const T zero = T(0);
+        const V4<T> none = zero4<T>();
+        X[SO] = zero4<T>();
+        update<CF_COLDIAG, 0>(cf, C[SO], X[SO], bO, X[SP], L3[SP], R0[SP], zero, zero, X[SE], L3[SE], R0[SE]);
+        R0[SO] = sl_dn1(X[SO].v[0]);
+        update<CF_ALL8, 1>(cf, C[SO], X[SO], bO, X[SP], L3[SP], R0[SP], zero, R0[SO], X[SE], L3[SE], R0[SE]);
+        L3[SO] = sl_up1(X[SO].v[3]);
+        R[SO] = zero4<T>();
+        resid<CF_ROW, 0>(cf, C[SO], R[SO], none, zero, zero, X[SO], L3[SO], R0[SO], none, zero, zero);
+    }
+    template <int SP, int SQ, int SO, typename CF> __device__ __forceinline__ void down_resid_even(const CF& cf) {
+        R[SP] = zero4<T>();
+        resid<CF_ALL8, 0>(cf, C[SP], R[SP], X[SQ], L3[SQ], R0[SQ], X[SP], L3[SP], R0[SP], X[SO], L3[SO], R0[SO]);
+        resid<CF_COLDIAG, 1>(cf, C[SP], R[SP], X[SQ], L3[SQ], R0[SQ], X[SP], L3[SP], R0[SP], X[SO], L3[SO], R0[SO]);
+    }
     template <int U> __device__ __forceinline__ void step_down(int j, int nsteps) {
         constexpr int SE = (2 * U + 2) % 12, SO = (2 * U + 1) % 12, SP = (2 * U) % 12, SQ = (2 * U + 11) % 12;
         constexpr int A5 = (2 * U + 5) % 12, A6 = (2 * U + 6) % 12, A7 = (2 * U + 7) % 12, A8 = (2 * U + 8) % 12;
@@ -221,33 +266,30 @@ struct CsWarp {
         sl_cp_wait<2>();
         const int rhoO = 2 * j + 1, rhoE = 2 * j + 2, rhoP = 2 * j;
         const V4<T> bO = rowA(rhoO), bE = rowA(rhoE);
-        const T zero = T(0);
-        const V4<T> none = zero4<T>();
-        // even row E: colours 0 and 1
-        X[SE] = zero4<T>();
-        update<0, 0>(rhoE, C[SE], X[SE], bE, none, zero, zero, zero, zero, none, zero, zero);
-        R0[SE] = sl_dn1(X[SE].v[0]);
-        update<CF_ROW, 1>(rhoE, C[SE], X[SE], bE, none, zero, zero, zero, R0[SE], none, zero, zero);
-        L3[SE] = sl_up1(X[SE].v[3]);
-        // odd row O: colours 2 and 3
-        X[SO] = zero4<T>();
-        update<CF_COLDIAG, 0>(rhoO, C[SO], X[SO], bO, X[SP], L3[SP], R0[SP], zero, zero, X[SE], L3[SE], R0[SE]);
-        R0[SO] = sl_dn1(X[SO].v[0]);
-        update<CF_ALL8, 1>(rhoO, C[SO], X[SO], bO, X[SP], L3[SP], R0[SP], zero, R0[SO], X[SE], L3[SE], R0[SE]);
-        L3[SO] = sl_up1(X[SO].v[3]);
+        // coefficients of rows E and O first (row O's are in flight while row E is swept), then the sweeps
+        const bool gE = any_general(C[SE]), gO = any_general(C[SO]);
+        if (gE | gO) {
+            CfQuad qE, qO;
+            load_quads<0x038>(qE, rhoE, C[SE]);
+            load_quads<0x1FF>(qO, rhoO, C[SO]);
+            down_even<SE>(qE, bE);                       // even row E: colours 0 and 1 (own row only)
+            down_odd<SO, SP, SE>(qO, bO);                // odd row O: colours 2 and 3, then its residual (colour 2)
+        } else {
+            down_even<SE>(CfRef{ref, inv_ref}, bE);
+            down_odd<SO, SP, SE>(CfRef{ref, inv_ref}, bO);
+        }
         // rows O and E are final
         const int rO = rbase + rhoO, rE = rbase + rhoE;
         if (own_row(rO) && C[SO]) st4(xk + ((long long)rO * pitch + c0), X[SO]);
         if (own_row(rE) && C[SE]) st4(xk + ((long long)rE * pitch + c0), X[SE]);
-        // residuals: colour 2 of row O; colours 0 and 1 of row P
-        R[SO] = zero4<T>();
-        resid<CF_ROW, 0>(rhoO, C[SO], R[SO], none, zero, zero, X[SO], L3[SO], R0[SO], none, zero, zero);
-        R[SP] = zero4<T>();
-        resid<CF_ALL8, 0>(rhoP, C[SP], R[SP], X[SQ], L3[SQ], R0[SQ], X[SP], L3[SP], R0[SP], X[SO], L3[SO], R0[SO]);
-        resid<CF_COLDIAG, 1>(rhoP, C[SP], R[SP], X[SQ], L3[SQ], R0[SQ], X[SP], L3[SP], R0[SP], X[SO], L3[SO], R0[SO]);
+        // residual of row P (colours 0 and 1)
+        if (any_general(C[SP])) { CfQuad q; load_quads<0x1EF>(q, rhoP, C[SP]); down_resid_even<SP, SQ, SO>(q); }
+        else down_resid_even<SP, SQ, SO>(CfRef{ref, inv_ref});
         // next-coarser row I on row P: full weighting (the diagonal neighbours are colour 3: zero residual)
         const T rl = sl_up1(R[SP].v[3]);
         const int rP = rbase + rhoP, I = rP >> 1;
+        const unsigned ccw = ccnext;                 // code bytes of the lane's two next-coarser pixels, loaded a step ago
+        ccnext = load_ccode(I + 1);
         if (rP >= i0 && rP < i0 + cr && I < crows && owner && colin) {
             const int Ja = c0 >> 1;
             if (Ja < ccols) {
@@ -257,7 +299,7 @@ struct CsWarp {
                 if (Ja + 1 >= ccols) vb = T(0);
                 const long long oc = (long long)I * cpitch + Ja;
                 // inactive next-coarser pixels keep the zeros they were created with
-                if (*reinterpret_cast<const unsigned short*>(ccode + oc)) sts2(cb + oc, va, vb);
+                if (ccw) sts2(cb + oc, va, vb);
             }
         }
     }
@@ -270,6 +312,7 @@ struct CsWarp {
         for (int q = 1; q <= 6; ++q) C[q] = load_code(q);
         request(1, C[1], C[2]);
         request(3, C[3], C[4]);
+        ccnext = load_ccode(rbase >> 1);             // step 0's row P is relative row 0
 #pragma unroll 1
         for (int jb = 0; jb < nsteps; jb += 6) {
             step_down<0>(jb, nsteps); step_down<1>(jb + 1, nsteps); step_down<2>(jb + 2, nsteps);
@@ -290,6 +333,17 @@ struct CsWarp {
         }
         EA[SLOT][0] = a; EA[SLOT][1] = b;
         EA[SLOT][2] = sl_dn1(a);
+    }
+    template <int SO, int SP, int SE, typename CF> __device__ __forceinline__ void up_odd(const CF& cf, const V4<T>& bO) {
+        update<CF_ALL8, 1>(cf, C[SO], X[SO], bO, X[SP], L3[SP], R0[SP], L3[SO], R0[SO], X[SE], L3[SE], R0[SE]);
+        L3u[SO] = sl_up1(X[SO].v[3]);
+        update<CF_ALL8, 0>(cf, C[SO], X[SO], bO, X[SP], L3[SP], R0[SP], L3u[SO], R0[SO], X[SE], L3[SE], R0[SE]);
+        R0u[SO] = sl_dn1(X[SO].v[0]);
+    }
+    template <int SP, int SQ, int SO, typename CF> __device__ __forceinline__ void up_even(const CF& cf, const V4<T>& bP) {
+        update<CF_ALL8, 1>(cf, C[SP], X[SP], bP, X[SQ], L3u[SQ], R0u[SQ], L3[SP], R0[SP], X[SO], L3u[SO], R0u[SO]);
+        L3u[SP] = sl_up1(X[SP].v[3]);
+        update<CF_ALL8, 0>(cf, C[SP], X[SP], bP, X[SQ], L3u[SQ], R0u[SQ], L3u[SP], R0[SP], X[SO], L3u[SO], R0u[SO]);
     }
     template <int U> __device__ __forceinline__ void step_up(int j, int nsteps) {
         constexpr int SE = (2 * U + 2) % 12, SO = (2 * U + 1) % 12, SP = (2 * U) % 12, SQ = (2 * U + 11) % 12;
@@ -330,14 +384,11 @@ struct CsWarp {
         R0[SO] = sl_dn1(X[SO].v[0]); R0[SE] = sl_dn1(X[SE].v[0]);
         L3[SO] = sl_up1(X[SO].v[3]); L3[SE] = sl_up1(X[SE].v[3]);
         // odd row O: colours 3 then 2; rows P and E are still un-swept
-        update<CF_ALL8, 1>(rhoO, C[SO], X[SO], bO, X[SP], L3[SP], R0[SP], L3[SO], R0[SO], X[SE], L3[SE], R0[SE]);
-        L3u[SO] = sl_up1(X[SO].v[3]);
-        update<CF_ALL8, 0>(rhoO, C[SO], X[SO], bO, X[SP], L3[SP], R0[SP], L3u[SO], R0[SO], X[SE], L3[SE], R0[SE]);
-        R0u[SO] = sl_dn1(X[SO].v[0]);
+        if (any_general(C[SO])) { CfQuad q; load_quads<0x1FF>(q, rhoO, C[SO]); up_odd<SO, SP, SE>(q, bO); }
+        else up_odd<SO, SP, SE>(CfRef{ref, inv_ref}, bO);
         // even row P: colours 1 then 0; rows Q and O are swept
-        update<CF_ALL8, 1>(rhoP, C[SP], X[SP], bP, X[SQ], L3u[SQ], R0u[SQ], L3[SP], R0[SP], X[SO], L3u[SO], R0u[SO]);
-        L3u[SP] = sl_up1(X[SP].v[3]);
-        update<CF_ALL8, 0>(rhoP, C[SP], X[SP], bP, X[SQ], L3u[SQ], R0u[SQ], L3u[SP], R0[SP], X[SO], L3u[SO], R0u[SO]);
+        if (any_general(C[SP])) { CfQuad q; load_quads<0x1FF>(q, rhoP, C[SP]); up_even<SP, SQ, SO>(q, bP); }
+        else up_even<SP, SQ, SO>(CfRef{ref, inv_ref}, bP);
         const int rO = rbase + rhoO, rP = rbase + rhoP;
         if (own_row(rP) && C[SP]) st4(xk + ((long long)rP * pitch + c0), X[SP]);
         if (own_row(rO) && C[SO]) st4(xk + ((long long)rO * pitch + c0), X[SO]);
@@ -363,16 +414,16 @@ struct CsWarp {
 };
 
 // this lane's slot-0 quad in ring `which` of the warp (dynamic shared memory: [which][warp][CS_RING][128] T)
-template <typename T> __device__ __forceinline__ T* cs_ring(int which) {
+template <typename T, bool UP> __device__ __forceinline__ T* cs_ring(int which) {
     extern __shared__ __align__(16) unsigned char sl_smem[];
-    return reinterpret_cast<T*>(sl_smem) + (((which * CsCfg<T>::WPB + (threadIdx.x >> 5)) * CS_RING) * 32 + (threadIdx.x & 31)) * 4;
+    return reinterpret_cast<T*>(sl_smem) + (((which * CsCfg<T, UP>::WPB + (threadIdx.x >> 5)) * CS_RING) * 32 + (threadIdx.x & 31)) * 4;
 }
 
 template <typename T, bool UP>
-__global__ void __launch_bounds__(32 * CsCfg<T>::WPB, 1)
+__global__ void __launch_bounds__(32 * CsCfg<T, UP>::WPB, 1)
 cs_leg_kernel(Coarse<T> L, Coarse<T> Lc, int have_coarse, const uint8_t* __restrict__ act, int cr, int ns, int nchunks, const int* __restrict__ done) {
     if (done && *done) return;
-    const int wid = blockIdx.x * CsCfg<T>::WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;     // warp <-> (chunk, channel)
+    const int wid = blockIdx.x * CsCfg<T, UP>::WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;     // warp <-> (chunk, channel)
     const int idx = wid / L.K, k = wid - idx * L.K;
     if (idx >= nchunks) return;
     if (!(act[idx] & (UP ? 1 : 2))) return;
@@ -381,17 +432,22 @@ cs_leg_kernel(Coarse<T> L, Coarse<T> Lc, int have_coarse, const uint8_t* __restr
     w.code = L.code; w.coef = L.coef; w.plane = L.plane; w.rows = L.rows; w.pitch = L.pitch;
 #pragma unroll
     for (int n = 0; n < 9; ++n) w.ref[n] = L.ref[n];
-    w.inv_ref = L.has_ref ? T(1) / L.ref[4] : T(0);
+    w.inv_ref = L.has_ref ? cs_rcp(L.ref[4]) : T(0);
+    w.refq = L.refq;
     w.c0 = s * CS_OUT - 4 + 4 * lane;
     w.i0 = t * cr; w.cr = cr; w.rbase = w.i0 - 4;
     w.colin = w.c0 >= 0 && w.c0 < L.pitch;
     w.owner = lane >= 1 && lane <= 30;
     w.xk = (UP ? L.x2 : L.x) + k * L.plane;      // (up: to the second buffer -- neighbouring chunks read the pre-smoothed x as halo)
-    w.ringA = cs_ring<T>(0);
+    w.ringA = cs_ring<T, UP>(0);
+    {
+        extern __shared__ __align__(16) unsigned char sl_smem[];
+        w.scratch = reinterpret_cast<float*>(sl_smem + (size_t)(UP ? 2 : 1) * CsCfg<T, UP>::WPB * CS_RING * 128 * sizeof(T)) + threadIdx.x;
+    }
     w.ccode = Lc.code; w.crows = Lc.rows; w.ccols = Lc.cols; w.cpitch = Lc.pitch;
     if (UP) {
         w.pa = L.x + k * L.plane; w.pb = L.b + k * L.plane;
-        w.ringB = cs_ring<T>(1);
+        w.ringB = cs_ring<T, UP>(1);
         w.ce = have_coarse ? Lc.x + k * Lc.plane : nullptr;
         w.cb = nullptr;
         w.run_up();

@@ -426,7 +426,7 @@ struct Solver : SolverBase {
     // ---- multigrid ----------------------------------------------------------------------------
     void free_hierarchy() {
         for (auto* lv : {&coarse, &gcoarse}) {
-            for (auto& c : *lv) { cudaFree(c.coef); cudaFree(c.x); cudaFree(c.x2); cudaFree(c.b); cudaFree(c.code); cudaFree(c.act_up); cudaFree(c.act_down); cudaFree(c.cs_act); }
+            for (auto& c : *lv) { cudaFree(c.coef); cudaFree(c.x); cudaFree(c.x2); cudaFree(c.b); cudaFree(c.code); cudaFree(c.act_up); cudaFree(c.act_down); cudaFree(c.cs_act); cudaFree(c.refq); }
             lv->clear();
         }
         cudaFree(d_dense); cudaFree(d_gdense);
@@ -452,6 +452,7 @@ struct Solver : SolverBase {
         L.coef = L.x = L.b = L.x2 = nullptr;
         L.code = L.act_up = L.act_down = nullptr;
         L.cs_act = nullptr; L.cs_cr = L.cs_ns = L.cs_nt = 0;
+        L.refq = nullptr;
         L.tiles_x = (L.pitch + CF_TX - 1) / CF_TX;
         L.tiles_y = (L.rows + CF_TY - 1) / CF_TY;
         L.has_ref = 0;
@@ -499,7 +500,7 @@ struct Solver : SolverBase {
             else galerkin_kernel<T, CoarseAcc<T>><<<cg, 128, 0, stream>>>(CoarseAcc<T>{lv.back()}, L);
             lv.push_back(L);
             for (int c = 0; c < 9; ++c)
-                cudaMemcpyAsync(&ref_stencil[l][c], L.coef + (long long)c * L.plane + (long long)(m / 2) * L.pitch + m / 2, sizeof(T),
+                cudaMemcpyAsync(&ref_stencil[l][c], L.coef + cidx(c, (long long)(m / 2) * L.pitch + m / 2), sizeof(T),
                                 cudaMemcpyDeviceToHost, stream);
         }
         if (err == cudaSuccess) err = cudaStreamSynchronize(stream);
@@ -529,16 +530,18 @@ struct Solver : SolverBase {
             L.cs_nt = (L.rows + L.cs_cr - 1) / L.cs_cr;
             CU(cudaMalloc(&L.cs_act, (size_t)L.cs_ns * L.cs_nt));
             cs_activity_kernel<<<dim3(L.cs_ns, L.cs_nt), 256, 0, stream>>>(L.code, L.rows, L.cols, L.pitch, L.cs_cr, L.cs_ns, L.cs_act);
+            CU(cudaMalloc(&L.refq, 36 * sizeof(T)));
+            cs_refq_kernel<T><<<1, 64, 0, stream>>>(L);
         }
         return HG_OK;
     }
     bool coarse_tiles = getenv("HGRID_COARSE_TILES") != nullptr;     // A/B aid: the shared-memory tile legs of coarse_fused.cuh on every level
     template <bool UP>
     void launch_cs(const Coarse<T>& L, const Coarse<T>& Lc, const int* done) {
-        constexpr int WPB = CsCfg<T>::WPB;
+        constexpr int WPB = CsCfg<T, UP>::WPB;
         const int nchunks = L.cs_ns * L.cs_nt;
         const unsigned blocks = (unsigned)(((long long)nchunks * K + WPB - 1) / WPB);
-        const size_t sm = (size_t)(UP ? 2 : 1) * WPB * CS_RING * 128 * sizeof(T);
+        const size_t sm = (size_t)(UP ? 2 : 1) * WPB * CS_RING * 128 * sizeof(T) + 32 * WPB * sizeof(float);   // rings + scratch words
         cs_leg_kernel<T, UP><<<blocks, 32 * WPB, sm, stream>>>(L, Lc, 1, L.cs_act, L.cs_cr, L.cs_ns, nchunks, done);
     }
 
@@ -546,8 +549,8 @@ struct Solver : SolverBase {
     int set_fused_attrs() {
         CU(cudaFuncSetAttribute(cdown_kernel<T, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CFSmem<T, KC, false>)));
         CU(cudaFuncSetAttribute(cup_kernel<T, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CFSmem<T, KC, true>)));
-        CU(cudaFuncSetAttribute(cs_leg_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * CsCfg<T>::WPB * CS_RING * 128 * sizeof(T))));
-        CU(cudaFuncSetAttribute(cs_leg_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CsCfg<T>::WPB * CS_RING * 128 * sizeof(T))));
+        CU(cudaFuncSetAttribute(cs_leg_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * CsCfg<T, true>::WPB * CS_RING * 128 * sizeof(T) + 32 * CsCfg<T, true>::WPB * sizeof(float))));
+        CU(cudaFuncSetAttribute(cs_leg_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CsCfg<T, false>::WPB * CS_RING * 128 * sizeof(T) + 32 * CsCfg<T, false>::WPB * sizeof(float))));
         return HG_OK;
     }
     template <int KC>
@@ -640,7 +643,7 @@ struct Solver : SolverBase {
         Coarse<T> G;
         HGTRY(alloc_level(G, chain(global_rows, HG_GATHER_LEVEL), Ll.cols));
         if (G.pitch != Ll.pitch) return fail(HG_ERR_INVALID, "slab mode: pitch mismatch at the gather level");
-        HGTRY(gather_level(Ll.coef, Ll.plane, G.coef, G.plane, G.pitch, 9));
+        HGTRY(gather_level(Ll.coef, 0, G.coef, 0, 9 * G.pitch, 1));     // (quad-interleaved: a row of the level is 9 * pitch contiguous values)
         HGTRY(finish_level(G, HG_GATHER_LEVEL));
         gcoarse.push_back(G);
         int r = G.rows, c = G.cols;
@@ -1182,7 +1185,7 @@ struct Solver : SolverBase {
             for (int c = 0; c < 9; ++c)
                 for (int i = 0; i < L.rows; ++i)
                     for (int j = 0; j < L.cols; ++j)
-                        coef9[((size_t)i * L.cols + j) * 9 + c] = (double)tmp[(size_t)c * L.plane + (size_t)i * L.pitch + j];
+                        coef9[((size_t)i * L.cols + j) * 9 + c] = (double)tmp[(size_t)cidx(c, (long long)i * L.pitch + j)];
         }
         return HG_OK;
     }

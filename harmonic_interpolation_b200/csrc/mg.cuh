@@ -19,8 +19,12 @@
 
 namespace hg {
 
-// explicit 9-point level; coef plane c = (di+1)*3 + (dj+1), centre plane 4.
+// explicit 9-point level; coefficient c = (di+1)*3 + (dj+1), centre 4.  Storage is interleaved by QUAD of four
+// consecutive pixels of a row: [quad][9][4] -- the nine coefficient vectors of a quad are 144 contiguous bytes (fp32),
+// which is what a lane of the streaming legs (coarse_stream.cuh) needs for a row, and a general quad costs 5 sectors
+// of HBM traffic instead of 9.  cidx(c, o) is the element index of coefficient c of pixel offset o = i * pitch + j.
 // A pixel whose centre coefficient is 0 is inactive (x stays 0 there).
+__host__ __device__ __forceinline__ long long cidx(int c, long long o) { return (o >> 2) * 36 + c * 4 + (o & 3); }
 template <typename T>
 struct Coarse {
     int rows, cols, pitch;
@@ -42,6 +46,7 @@ struct Coarse {
     // streaming legs (coarse_stream.cuh): chunks of 120 columns x cs_cr rows, activity bits per chunk; cs_cr == 0: tile legs
     uint8_t* cs_act;
     int cs_cr, cs_ns, cs_nt;
+    T* refq;   // ref[n] four times over (n * 4 + p): what a lane without a general pixel reads in place of the planes
 };
 
 // ---- transfer weights ---------------------------------------------------------------------
@@ -114,10 +119,10 @@ struct CoarseAcc {          // explicit 9-point operator
     __device__ __forceinline__ int pitch() const { return c.pitch; }
     __device__ __forceinline__ long long plane() const { return c.plane; }
     __device__ __forceinline__ bool active(int i, int j) const {
-        return i >= 0 && i < c.rows && j >= 0 && j < c.cols && c.coef[4 * c.plane + (long long)i * c.pitch + j] != T(0);
+        return i >= 0 && i < c.rows && j >= 0 && j < c.cols && c.coef[cidx(4, (long long)i * c.pitch + j)] != T(0);
     }
     __device__ __forceinline__ double entry(int i, int j, int di, int dj) const {
-        return (double)c.coef[((di + 1) * 3 + (dj + 1)) * c.plane + (long long)i * c.pitch + j];
+        return (double)c.coef[cidx((di + 1) * 3 + (dj + 1), (long long)i * c.pitch + j)];
     }
     __device__ __forceinline__ T apply(const T* x, int i, int j) const {
         const long long o = (long long)i * c.pitch + j;
@@ -126,7 +131,7 @@ struct CoarseAcc {          // explicit 9-point operator
         for (int di = -1; di <= 1; ++di)
 #pragma unroll
             for (int dj = -1; dj <= 1; ++dj) {
-                const T a = c.coef[((di + 1) * 3 + (dj + 1)) * c.plane + o];
+                const T a = c.coef[cidx((di + 1) * 3 + (dj + 1), o)];
                 if (a != T(0)) v += a * x[o + (long long)di * c.pitch + dj];   // a == 0 outside the grid
             }
         return v;
@@ -174,7 +179,7 @@ __global__ void galerkin_kernel(Acc fine, Coarse<T> cl) {
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
-        for (int b = 0; b < 3; ++b) cl.coef[(a * 3 + b) * cl.plane + oc] = (T)acc[a][b];
+        for (int b = 0; b < 3; ++b) cl.coef[cidx(a * 3 + b, oc)] = (T)acc[a][b];
 }
 
 // ---- level-0 red-black Gauss-Seidel, one colour per launch -------------------------------------
@@ -214,11 +219,11 @@ mcgs_kernel(Coarse<T> L, int colour, const int* __restrict__ done) {
     const long long o = (long long)i * L.pitch + j;
     // inactive pixels (inside fully constrained areas) are decided on the centre coefficient alone,
     // before the other eight planes are touched
-    const T c4 = L.coef[4 * L.plane + o];
+    const T c4 = L.coef[cidx(4, o)];
     if (!(c4 > T(0))) return;
     T cf[9];
 #pragma unroll
-    for (int c = 0; c < 9; ++c) cf[c] = c == 4 ? c4 : L.coef[c * L.plane + o];
+    for (int c = 0; c < 9; ++c) cf[c] = c == 4 ? c4 : L.coef[cidx(c, o)];
     const T inv = T(1) / c4;
     for (int k = 0; k < L.K; ++k) {
         T* xk = L.x + k * L.plane;
@@ -252,14 +257,14 @@ coarsest_kernel(Coarse<T> L, int sweeps, const int* __restrict__ done) {
                     const int i = e / L.cols, j = e % L.cols;
                     if ((((i & 1) << 1) | (j & 1)) != colour) continue;
                     const long long o = (long long)i * L.pitch + j;
-                    const T c4 = L.coef[4 * L.plane + o];
+                    const T c4 = L.coef[cidx(4, o)];
                     if (!(c4 > T(0))) continue;
                     T v = bk[o];
                     for (int di = -1; di <= 1; ++di)
                         for (int dj = -1; dj <= 1; ++dj) {
                             const int c = (di + 1) * 3 + (dj + 1);
                             if (c == 4) continue;
-                            const T a = L.coef[c * L.plane + o];
+                            const T a = L.coef[cidx(c, o)];
                             if (a != T(0)) v -= a * xk[o + (long long)di * L.pitch + dj];
                         }
                     xk[o] = v / c4;
@@ -281,7 +286,7 @@ resid_restrict_kernel(Acc fine, const T* __restrict__ xf, const T* __restrict__ 
     const int I = blockIdx.y;
     if (J >= cl.pitch) return;
     const long long oc = (long long)I * cl.pitch + J;
-    const bool live = J < cl.cols && cl.coef[4 * cl.plane + oc] != T(0);
+    const bool live = J < cl.cols && cl.coef[cidx(4, oc)] != T(0);
     const int nfr = fine.rows(), nfc = fine.cols();
     for (int k = 0; k < K; ++k) {
         double s = 0.0;
@@ -345,15 +350,15 @@ __global__ void dense_fill_kernel(Coarse<T> L, double* __restrict__ M) {
     const long long o = (long long)i * L.pitch + j;
     double* row = M + (long long)e * 2 * n;
     row[n + e] = 1.0;
-    const T c4 = L.coef[4 * L.plane + o];
+    const T c4 = L.coef[cidx(4, o)];
     if (!(c4 > T(0))) { row[e] = 1.0; return; }
     for (int di = -1; di <= 1; ++di)
         for (int dj = -1; dj <= 1; ++dj) {
-            const T a = L.coef[((di + 1) * 3 + (dj + 1)) * L.plane + o];
+            const T a = L.coef[cidx((di + 1) * 3 + (dj + 1), o)];
             if (a == T(0)) continue;
             const int qi = i + di, qj = j + dj;
             // couplings to inactive pixels are dropped: their value is held at 0
-            if (L.coef[4 * L.plane + (long long)qi * L.pitch + qj] > T(0)) row[qi * L.cols + qj] = (double)a;
+            if (L.coef[cidx(4, (long long)qi * L.pitch + qj)] > T(0)) row[qi * L.cols + qj] = (double)a;
         }
 }
 // Gauss-Jordan without pivoting, one block.  The matrix is symmetric positive SEMI-definite:
