@@ -47,6 +47,7 @@ SYMBOLS = {
     "hg_device_count": (ctypes.c_int, []),
     "hg_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_H)]),
     "hg_destroy": (ctypes.c_int, [_H]),
+    "hg_trim_memory": (ctypes.c_int, []),
     "hg_set_flags": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_uint8)]),
     "hg_set_soft_weights": (ctypes.c_int, [_H, _dp, ctypes.c_double]),
     "hg_set_grad_weight": (ctypes.c_int, [_H, ctypes.c_double]),

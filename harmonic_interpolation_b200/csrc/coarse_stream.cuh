@@ -38,8 +38,12 @@ namespace hg {
 
 #define CS_OUT 120
 #define CS_RING 8                       // rows of the shared-memory FIFO (row <-> slot row & 7)
-// warps per block: the pipeline state of a warp is ~165 registers (fp32), so one block per SM: 12 warps (fp32) / 8 (fp64)
-template <typename T, bool UP> struct CsCfg { static constexpr int WPB = sizeof(T) == 4 ? 12 : 8; };
+// warps per block (one block per SM): the pipeline state of a warp is ~165 registers (fp32); 16 warps at 128 registers with
+// a few hundred bytes of spills measured faster than 12 warps without (the legs are latency-bound: occupancy wins)
+#ifndef CS_WPB32
+#define CS_WPB32 16
+#endif
+template <typename T, bool UP> struct CsCfg { static constexpr int WPB = sizeof(T) == 4 ? CS_WPB32 : 8; };
 // Brings a line into L1 without a register destination (a load into a dummy register makes the next writer of that
 // register wait for HBM; prefetch.global.L1 gave no measurable hit rate): a 4-byte cp.async.ca into a scratch word.
 __device__ __forceinline__ void cs_touch(const void* gmem, void* scratch) {

@@ -74,6 +74,57 @@ __global__ void sl_activity_kernel(const uint8_t* __restrict__ flags, const uint
     if (threadIdx.x == 0) active[blockIdx.y * ns + blockIdx.x] = (uint8_t)(any ? (general ? 2 : 1) : 0);
 }
 
+// Task lists of the streaming kernels, built on the device (one block per list, ordered compaction: chunk order is kept, so
+// the lists -- and with them every launch -- are the same from run to run): list `which` = [down lean | down general |
+// up lean | up general] at lists + which * n; counts[which] = its length.  split (slab mode with overlap): the down
+// lists hold the interior chunks first, then those whose rows touch a ghost band; counts[4 + which] = number of interior ones.
+__global__ void __launch_bounds__(1024)
+sl_task_lists_kernel(const uint8_t* __restrict__ up, const uint8_t* __restrict__ down, int n, int ns, int rows, int ghost_top,
+                     int ghost_bottom, int split, int* __restrict__ lists, int* __restrict__ counts) {
+    const int which = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint8_t* a = which < 2 ? down : up;
+    const unsigned want = (which & 1) ? 2u : 1u;
+    int* out = lists + (long long)which * n;
+    __shared__ int wsum[32];
+    __shared__ int base, total;
+    if (tid == 0) base = 0;
+    __syncthreads();
+    const int passes = (split && which < 2) ? 2 : 1;
+    for (int pass = 0; pass < passes; ++pass) {
+        for (int e0 = 0; e0 < n; e0 += 1024) {
+            const int e = e0 + tid;
+            bool sel = e < n && a[e] == want;
+            if (sel && passes == 2) {
+                // a down task is a boundary task if its rows 64 t - 3 .. 64 t + 66 touch a ghost band
+                const int t = e / ns;
+                const bool bnd = (ghost_top > 0 && SL_R * t - 3 < ghost_top) || (ghost_bottom > 0 && SL_R * t + SL_R + 2 >= rows - ghost_bottom);
+                sel = bnd == (pass == 1);
+            }
+            const unsigned bal = __ballot_sync(HG_FULL, sel);
+            if (lane == 0) wsum[warp] = __popc(bal);
+            __syncthreads();
+            if (warp == 0) {
+                const int v = wsum[lane];
+                int inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(HG_FULL, inc, o);
+                    if (lane >= o) inc += u;
+                }
+                wsum[lane] = inc - v;
+                if (lane == 31) total = inc;
+            }
+            __syncthreads();
+            if (sel) out[base + wsum[warp] + __popc(bal & ((1u << lane) - 1u))] = e;
+            __syncthreads();
+            if (tid == 0) base += total;
+            __syncthreads();
+        }
+        if (pass == 0 && tid == 0 && which < 2) counts[4 + which] = base;
+    }
+    if (tid == 0) counts[which] = base;
+}
+
 template <typename T> __device__ __forceinline__ T sl_up1(T v) { return __shfl_up_sync(HG_FULL, v, 1); }
 template <typename T> __device__ __forceinline__ T sl_dn1(T v) { return __shfl_down_sync(HG_FULL, v, 1); }
 

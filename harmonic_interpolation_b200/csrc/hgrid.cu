@@ -149,6 +149,13 @@ struct Solver : SolverBase {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
+    // Device memory comes from the device's default stream-ordered pool (cudaMallocAsync), whose release threshold init()
+    // raises to "never": a solver's tens of GB are mapped once per process, later solvers of the process reuse them, and
+    // destruction does not pay for unmapping (cudaMalloc / cudaFree of a 16384^2 solver cost 0.4 s + 0.2 .. 1 s).
+    // hg_trim_memory() hands the cached memory back to the driver.
+    template <typename P> cudaError_t dmalloc(P** p, size_t n) { return cudaMallocAsync(reinterpret_cast<void**>(p), n ? n : 1, stream); }
+    cudaError_t dfree(void* p) { return p ? cudaFreeAsync(p, stream) : cudaSuccess; }
+
     uint8_t* d_flags = nullptr;
     T* d_soft = nullptr;
     T* d_dinv = nullptr;
@@ -258,6 +265,17 @@ struct Solver : SolverBase {
     bool no_fuse = getenv("HGRID_FUSE") == nullptr;      // the fused loop is opt-in (HGRID_FUSE=1): it does not pay yet
     int sl_ns = 0, sl_nt = 0;
     int* d_sl_tasks = nullptr;
+    int* d_task_counts = nullptr;
+    bool task_counts_pending = false;
+    int finish_task_lists() {      // after a stream sync: the list lengths the launches need
+        if (!task_counts_pending) return HG_OK;
+        int c[8];
+        CU(cudaMemcpy(c, d_task_counts, sizeof c, cudaMemcpyDeviceToHost));
+        sl_n_down_lean = c[0]; sl_n_down_gen = c[1]; sl_n_up_lean = c[2]; sl_n_up_gen = c[3];
+        sl_n_int[0] = c[4]; sl_n_int[1] = c[5];
+        task_counts_pending = false;
+        return HG_OK;
+    }
     int sl_off[4] = {0, 0, 0, 0}, sl_n_down_lean = 0, sl_n_down_gen = 0, sl_n_up_lean = 0, sl_n_up_gen = 0;
     bool tile_legs = getenv("HGRID_TILE_LEGS") != nullptr;       // debugging aid: the shared-memory legs of fine_vec.cuh
     bool scalar_legs = getenv("HGRID_SCALAR_LEGS") != nullptr;
@@ -271,18 +289,18 @@ struct Solver : SolverBase {
     }
 
     ~Solver() override {
-        cudaFree(d_flags); cudaFree(d_soft); cudaFree(d_dinv);
-        cudaFree(d_x); cudaFree(d_b); cudaFree(d_r); cudaFree(d_p); cudaFree(d_q);
-        for (auto& p : d_stage) cudaFree(p);
-        cudaFree(d_out); cudaFree(d_part0); cudaFree(d_part1); cudaFree(d_state); cudaFree(d_presum); cudaFree(d_counts);
+        dfree(d_flags); dfree(d_soft); dfree(d_dinv); dfree(d_raw);
+        dfree(d_x); dfree(d_b); dfree(d_r); dfree(d_p); dfree(d_q);
+        for (auto& p : d_stage) dfree(p);
+        dfree(d_out); dfree(d_part0); dfree(d_part1); dfree(d_state); dfree(d_presum); dfree(d_counts);
         free_hierarchy();
-        cudaFree(d_z);
-        if (kRefine) { cudaFree(d_xm); cudaFree(d_bm); }
-        cudaFree(d_tile_active); cudaFree(d_tpart0); cudaFree(d_tpart1);
-        cudaFree(d_down_active); cudaFree(d_code); cudaFree(d_lpart);
-        cudaFree(d_sl_up); cudaFree(d_sl_down); cudaFree(d_spart); cudaFree(d_spart2); cudaFree(d_sl_tasks);
-        cudaFree(d_p2); cudaFree(d_r2); cudaFree(d_spart3); cudaFree(d_changed);
-        cudaFree(d_gl_rows); cudaFree(d_gsend);
+        dfree(d_z);
+        if (kRefine) { dfree(d_xm); dfree(d_bm); }
+        dfree(d_tile_active); dfree(d_tpart0); dfree(d_tpart1);
+        dfree(d_down_active); dfree(d_code); dfree(d_lpart);
+        dfree(d_sl_up); dfree(d_sl_down); dfree(d_spart); dfree(d_spart2); dfree(d_sl_tasks); dfree(d_task_counts);
+        dfree(d_p2); dfree(d_r2); dfree(d_spart3); dfree(d_changed);
+        dfree(d_gl_rows); dfree(d_gsend);
         if (comm && g_nccl.ok) g_nccl.CommDestroy(comm);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -293,6 +311,14 @@ struct Solver : SolverBase {
     }
 
     int init() {
+        {
+            int dev = 0;
+            CU(cudaGetDevice(&dev));
+            cudaMemPool_t pool = nullptr;
+            CU(cudaDeviceGetDefaultMemPool(&pool, dev));
+            unsigned long long keep = ~0ULL;
+            CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
         CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CU(cudaEventCreate(&ev0));
         CU(cudaEventCreate(&ev1));
@@ -301,10 +327,10 @@ struct Solver : SolverBase {
             CU(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&ev_arrived, cudaEventDisableTiming));
         }
-        CU(cudaMalloc(&d_flags, plane));
-        CU(cudaMalloc(&d_state, sizeof(CgState)));
-        CU(cudaMalloc(&d_presum, (size_t)HG_MAXK * PRESUM_BLOCKS * sizeof(double)));
-        CU(cudaMalloc(&d_counts, 8 * sizeof(unsigned long long)));
+        CU(dmalloc(&d_flags, plane));
+        CU(dmalloc(&d_state, sizeof(CgState)));
+        CU(dmalloc(&d_presum, (size_t)HG_MAXK * PRESUM_BLOCKS * sizeof(double)));
+        CU(dmalloc(&d_counts, 8 * sizeof(unsigned long long)));
         return HG_OK;
     }
 
@@ -338,19 +364,15 @@ struct Solver : SolverBase {
         ++launches;
     }
 
+    uint8_t* d_raw = nullptr;     // rows * cols bytes as the caller holds them (flags; also the uint8 image of hg_solve_u8)
     int set_flags(const uint8_t* f) override {
         if (!f) return fail(HG_ERR_INVALID, "hg_set_flags: NULL flags");
-        // sanitise on the way in: edge bits that point outside the grid are dropped, padding is hard
-        std::vector<uint8_t> tmp((size_t)plane, (uint8_t)HG_FLAG_HARD);
-        for (int i = 0; i < rows; ++i) {
-            uint8_t* dst = tmp.data() + (size_t)i * pitch;
-            memcpy(dst, f + (size_t)i * cols, cols);
-            if (i == rows - 1)
-                for (int j = 0; j < cols; ++j) dst[j] &= ~(HG_FLAG_CUT_DOWN | HG_FLAG_PEN_DOWN);
-            dst[cols - 1] &= ~(HG_FLAG_CUT_RIGHT | HG_FLAG_PEN_RIGHT);
-        }
-        CU(cudaMemcpyAsync(d_flags, tmp.data(), plane, cudaMemcpyHostToDevice, stream));
-        CU(cudaStreamSynchronize(stream));
+        // one contiguous upload; padding (hard) and the sanitising -- edge bits that point outside the grid are dropped -- on the device
+        const size_t n = (size_t)rows * cols;
+        if (!d_raw) CU(dmalloc(&d_raw, n * (size_t)std::max(K, 1)));
+        CU(cudaMemcpyAsync(d_raw, f, n, cudaMemcpyHostToDevice, stream));
+        pad_flags_kernel<<<dim3((pitch + 255) / 256, rows), 256, 0, stream>>>(d_raw, d_flags, rows, cols, pitch);
+        CU(cudaStreamSynchronize(stream));       // (the caller may reuse its buffer)
         flags_set = true;
         is_setup = false;
         return HG_OK;
@@ -359,14 +381,14 @@ struct Solver : SolverBase {
     int set_soft(const double* w, double scalar) override {
         soft_scalar = scalar;
         if (!w) {
-            cudaFree(d_soft);
+            dfree(d_soft);
             d_soft = nullptr;
             soft_plane_set = false;
         } else {
             std::vector<T> tmp((size_t)plane, T(0));
             for (int i = 0; i < rows; ++i)
                 for (int j = 0; j < cols; ++j) tmp[(size_t)i * pitch + j] = (T)w[(size_t)i * cols + j];
-            if (!d_soft) CU(cudaMalloc(&d_soft, plane * sizeof(T)));
+            if (!d_soft) CU(dmalloc(&d_soft, plane * sizeof(T)));
             CU(cudaMemcpyAsync(d_soft, tmp.data(), plane * sizeof(T), cudaMemcpyHostToDevice, stream));
             CU(cudaStreamSynchronize(stream));
             soft_plane_set = true;
@@ -400,23 +422,23 @@ struct Solver : SolverBase {
         T** v[] = {&d_x, &d_b, &d_r, &d_p, &d_q};
         for (T** p : v)
             if (!*p) {
-                CU(cudaMalloc(p, bytes));
+                CU(dmalloc(p, bytes));
                 CU(cudaMemsetAsync(*p, 0, bytes, stream));
             }
-        if (!d_dinv) CU(cudaMalloc(&d_dinv, plane * sizeof(T)));
+        if (!d_dinv) CU(dmalloc(&d_dinv, plane * sizeof(T)));
         if (kRefine) {
-            if (!d_xm) CU(cudaMalloc(&d_xm, (size_t)plane * K * sizeof(double)));
-            if (!d_bm) CU(cudaMalloc(&d_bm, (size_t)plane * K * sizeof(double)));
+            if (!d_xm) CU(dmalloc(&d_xm, (size_t)plane * K * sizeof(double)));
+            if (!d_bm) CU(dmalloc(&d_bm, (size_t)plane * K * sizeof(double)));
         } else {
             d_xm = reinterpret_cast<double*>(d_x);
             d_bm = reinterpret_cast<double*>(d_b);
         }
         const int need = std::max(std::max(op_blocks(), vec_blocks()), ((pitch + 255) / 256) * rows) * K;
         if (need > part_cap) {
-            cudaFree(d_part0); cudaFree(d_part1);
+            dfree(d_part0); dfree(d_part1);
             d_part0 = d_part1 = nullptr;
-            CU(cudaMalloc(&d_part0, (size_t)need * sizeof(double)));
-            CU(cudaMalloc(&d_part1, (size_t)need * sizeof(double)));
+            CU(dmalloc(&d_part0, (size_t)need * sizeof(double)));
+            CU(dmalloc(&d_part1, (size_t)need * sizeof(double)));
             part_cap = need;
         }
         return HG_OK;
@@ -426,19 +448,19 @@ struct Solver : SolverBase {
     // ---- multigrid ----------------------------------------------------------------------------
     void free_hierarchy() {
         for (auto* lv : {&coarse, &gcoarse}) {
-            for (auto& c : *lv) { cudaFree(c.coef); cudaFree(c.x); cudaFree(c.x2); cudaFree(c.b); cudaFree(c.code); cudaFree(c.act_up); cudaFree(c.act_down); cudaFree(c.cs_act); cudaFree(c.refq); }
+            for (auto& c : *lv) { dfree(c.coef); dfree(c.x); dfree(c.x2); dfree(c.b); dfree(c.code); dfree(c.act_up); dfree(c.act_down); dfree(c.cs_act); dfree(c.refq); }
             lv->clear();
         }
-        cudaFree(d_dense); cudaFree(d_gdense);
+        dfree(d_dense); dfree(d_gdense);
         d_dense = d_gdense = nullptr;
         for (size_t l = 0; l < lev25.size(); ++l) {
-            cudaFree(lev25[l].coef); cudaFree(lev25[l].label); cudaFree(lev25[l].aggD); cudaFree(lev25[l].aggS);
-            if (l > 0) { cudaFree(lev25[l].x); cudaFree(lev25[l].b); cudaFree(lev25[l].x2); }
+            dfree(lev25[l].coef); dfree(lev25[l].label); dfree(lev25[l].aggD); dfree(lev25[l].aggS);
+            if (l > 0) { dfree(lev25[l].x); dfree(lev25[l].b); dfree(lev25[l].x2); }
         }
         lev25.clear();
-        cudaFree(d_dense25);
+        dfree(d_dense25);
         d_dense25 = nullptr;
-        cudaFree(d_z2);
+        dfree(d_z2);
         d_z2 = nullptr;
     }
 
@@ -457,13 +479,13 @@ struct Solver : SolverBase {
         L.tiles_y = (L.rows + CF_TY - 1) / CF_TY;
         L.has_ref = 0;
         for (T& v : L.ref) v = T(0);
-        CU(cudaMalloc(&L.code, (size_t)L.plane));
-        CU(cudaMalloc(&L.act_up, (size_t)L.tiles_x * L.tiles_y));
-        CU(cudaMalloc(&L.act_down, (size_t)L.tiles_x * L.tiles_y));
-        CU(cudaMalloc(&L.coef, (size_t)L.plane * 9 * sizeof(T)));
-        CU(cudaMalloc(&L.x, (size_t)L.plane * K * sizeof(T)));
-        CU(cudaMalloc(&L.b, (size_t)L.plane * K * sizeof(T)));
-        CU(cudaMalloc(&L.x2, (size_t)L.plane * K * sizeof(T)));
+        CU(dmalloc(&L.code, (size_t)L.plane));
+        CU(dmalloc(&L.act_up, (size_t)L.tiles_x * L.tiles_y));
+        CU(dmalloc(&L.act_down, (size_t)L.tiles_x * L.tiles_y));
+        CU(dmalloc(&L.coef, (size_t)L.plane * 9 * sizeof(T)));
+        CU(dmalloc(&L.x, (size_t)L.plane * K * sizeof(T)));
+        CU(dmalloc(&L.b, (size_t)L.plane * K * sizeof(T)));
+        CU(dmalloc(&L.x2, (size_t)L.plane * K * sizeof(T)));
         CU(cudaMemsetAsync(L.x2, 0, (size_t)L.plane * K * sizeof(T), stream));
         CU(cudaMemsetAsync(L.coef, 0, (size_t)L.plane * 9 * sizeof(T), stream));
         CU(cudaMemsetAsync(L.x, 0, (size_t)L.plane * K * sizeof(T), stream));
@@ -477,11 +499,19 @@ struct Solver : SolverBase {
     static constexpr int REF_LEVELS = 5;
     T ref_stencil[REF_LEVELS + 1][9];
     bool ref_ready = false;
+    // (process-wide cache per storage type: the values depend on nothing else)
+    struct RefCache { T st[REF_LEVELS + 1][9]; bool ready; };
+    static RefCache& ref_cache() { static RefCache c = {}; return c; }
     int build_ref_stencils() {
         if (ref_ready) return HG_OK;
+        if (ref_cache().ready) {
+            memcpy(ref_stencil, ref_cache().st, sizeof ref_stencil);
+            ref_ready = true;
+            return HG_OK;
+        }
         const int n = 256;
         uint8_t* f = nullptr;
-        CU(cudaMalloc(&f, (size_t)n * n));
+        CU(dmalloc(&f, (size_t)n * n));
         cudaMemsetAsync(f, 0, (size_t)n * n, stream);
         Grid<T> g;
         g.rows = g.cols = g.pitch = n; g.plane = (long long)n * n; g.K = 1;
@@ -493,7 +523,7 @@ struct Solver : SolverBase {
             memset(&L, 0, sizeof L);
             const int m = n >> l;
             L.rows = L.cols = m; L.pitch = round_up(m, 32); L.plane = (long long)m * L.pitch; L.K = 1;
-            err = cudaMalloc(&L.coef, (size_t)L.plane * 9 * sizeof(T));
+            err = dmalloc(&L.coef, (size_t)L.plane * 9 * sizeof(T));
             if (err != cudaSuccess) break;
             dim3 cg((L.pitch + 127) / 128, L.rows);
             if (l == 1) galerkin_kernel<T, FineAcc<T>><<<cg, 128, 0, stream>>>(FineAcc<T>{g}, L);
@@ -505,10 +535,12 @@ struct Solver : SolverBase {
         }
         if (err == cudaSuccess) err = cudaStreamSynchronize(stream);
         if (err == cudaSuccess) err = cudaGetLastError();
-        for (auto& L : lv) cudaFree(L.coef);
-        cudaFree(f);
+        for (auto& L : lv) dfree(L.coef);
+        dfree(f);
         CU(err);
         ref_ready = true;
+        memcpy(ref_cache().st, ref_stencil, sizeof ref_stencil);
+        ref_cache().ready = true;
         return HG_OK;
     }
 
@@ -528,9 +560,9 @@ struct Solver : SolverBase {
             const long long warps64 = (long long)L.cs_ns * ((L.rows + 63) / 64) * K;
             L.cs_cr = warps64 >= 148LL * 8 * 2 ? 64 : 16;
             L.cs_nt = (L.rows + L.cs_cr - 1) / L.cs_cr;
-            CU(cudaMalloc(&L.cs_act, (size_t)L.cs_ns * L.cs_nt));
+            CU(dmalloc(&L.cs_act, (size_t)L.cs_ns * L.cs_nt));
             cs_activity_kernel<<<dim3(L.cs_ns, L.cs_nt), 256, 0, stream>>>(L.code, L.rows, L.cols, L.pitch, L.cs_cr, L.cs_ns, L.cs_act);
-            CU(cudaMalloc(&L.refq, 36 * sizeof(T)));
+            CU(dmalloc(&L.refq, 36 * sizeof(T)));
             cs_refq_kernel<T><<<1, 64, 0, stream>>>(L);
         }
         return HG_OK;
@@ -590,7 +622,7 @@ struct Solver : SolverBase {
 
     int build_dense(const Coarse<T>& L, double** out) {
         const int n = L.rows * L.cols;
-        CU(cudaMalloc(out, (size_t)n * 2 * n * sizeof(double)));
+        CU(dmalloc(out, (size_t)n * 2 * n * sizeof(double)));
         dense_from_stencil_kernel<T><<<64, 256, 0, stream>>>(L, *out);
         dense_fill_kernel<T><<<(n + 127) / 128, 128, 0, stream>>>(L, *out);
         gauss_jordan_kernel<<<1, 1024, 2 * n * sizeof(double), stream>>>(*out, n);
@@ -613,10 +645,10 @@ struct Solver : SolverBase {
         for (int q = 0; q < world; ++q) maxrows = std::max(maxrows, gl_end(q) - gl_start(q));
         const size_t block = (size_t)nplanes * maxrows * pitch_;
         if (block * (world + 1) > gbuf_elems) {
-            cudaFree(d_gsend);
+            dfree(d_gsend);
             d_gsend = nullptr;
             gbuf_elems = block * (world + 1);
-            CU(cudaMalloc(&d_gsend, gbuf_elems * sizeof(T)));
+            CU(dmalloc(&d_gsend, gbuf_elems * sizeof(T)));
             d_grecv = d_gsend + block;
         } else {
             d_grecv = d_gsend + block;
@@ -635,7 +667,7 @@ struct Solver : SolverBase {
         {
             std::vector<int> gl(2 * world);
             for (int q = 0; q < world; ++q) { gl[2 * q] = gl_start(q); gl[2 * q + 1] = gl_end(q) - gl_start(q); }
-            if (!d_gl_rows) CU(cudaMalloc(&d_gl_rows, 2 * world * sizeof(int)));
+            if (!d_gl_rows) CU(dmalloc(&d_gl_rows, 2 * world * sizeof(int)));
             CU(cudaMemcpyAsync(d_gl_rows, gl.data(), 2 * world * sizeof(int), cudaMemcpyHostToDevice, stream));
             HGTRY(sync_watchful());
         }
@@ -668,7 +700,7 @@ struct Solver : SolverBase {
     int build_hierarchy25() {
         free_hierarchy();
         if (!d_z) {
-            CU(cudaMalloc(&d_z, (size_t)plane * K * sizeof(T)));
+            CU(dmalloc(&d_z, (size_t)plane * K * sizeof(T)));
             CU(cudaMemsetAsync(d_z, 0, (size_t)plane * K * sizeof(T), stream));
         }
         int r = rows, c = cols;
@@ -681,17 +713,17 @@ struct Solver : SolverBase {
             L.coef = L.x = L.b = nullptr;
             L.label = nullptr; L.aggD = nullptr; L.aggS = nullptr;
             L.x2 = nullptr;
-            CU(cudaMalloc(&L.coef, (size_t)L.plane * 25 * sizeof(T)));
+            CU(dmalloc(&L.coef, (size_t)L.plane * 25 * sizeof(T)));
             if (mg25_rowgs) {
                 T* alt = nullptr;
-                CU(cudaMalloc(&alt, (size_t)L.plane * K * sizeof(T)));
+                CU(dmalloc(&alt, (size_t)L.plane * K * sizeof(T)));
                 CU(cudaMemsetAsync(alt, 0, (size_t)L.plane * K * sizeof(T), stream));
                 if (level == 0) d_z2 = alt;
                 L.x2 = alt;
             }
             if (level > 0) {
-                CU(cudaMalloc(&L.x, (size_t)L.plane * K * sizeof(T)));
-                CU(cudaMalloc(&L.b, (size_t)L.plane * K * sizeof(T)));
+                CU(dmalloc(&L.x, (size_t)L.plane * K * sizeof(T)));
+                CU(dmalloc(&L.b, (size_t)L.plane * K * sizeof(T)));
                 CU(cudaMemsetAsync(L.x, 0, (size_t)L.plane * K * sizeof(T), stream));
                 CU(cudaMemsetAsync(L.b, 0, (size_t)L.plane * K * sizeof(T), stream));
             }
@@ -707,7 +739,7 @@ struct Solver : SolverBase {
         }
         const Lev25<T>& L = lev25.back();
         const int n = L.rows * L.cols;
-        CU(cudaMalloc(&d_dense25, (size_t)n * 2 * n * sizeof(double)));
+        CU(dmalloc(&d_dense25, (size_t)n * 2 * n * sizeof(double)));
         CU(cudaMemsetAsync(d_dense25, 0, (size_t)n * 2 * n * sizeof(double), stream));
         dense_fill25_kernel<T><<<(n + 127) / 128, 128, 0, stream>>>(L, d_dense25);
         gauss_jordan_kernel<<<1, 1024, 2 * n * sizeof(double), stream>>>(d_dense25, n);
@@ -716,9 +748,9 @@ struct Solver : SolverBase {
     }
     // clusters of stiffly coupled pixels of a level (mg25.cuh); leaves L.label == nullptr if there are none
     int build_aggregates(Lev25<T>& L, double ref_diag) {
-        if (!d_changed) CU(cudaMalloc(&d_changed, sizeof(int)));
-        CU(cudaMalloc(&L.label, (size_t)L.plane * sizeof(int)));
-        CU(cudaMalloc(&L.aggD, (size_t)L.plane * sizeof(double)));
+        if (!d_changed) CU(dmalloc(&d_changed, sizeof(int)));
+        CU(dmalloc(&L.label, (size_t)L.plane * sizeof(int)));
+        CU(dmalloc(&L.aggD, (size_t)L.plane * sizeof(double)));
         const T thr = (T)(mg25_agg_theta * ref_diag);
         dim3 pg((L.pitch + 255) / 256, L.rows);
         agg_label_init_kernel<T><<<pg, 256, 0, stream>>>(L, thr);
@@ -734,22 +766,22 @@ struct Solver : SolverBase {
         int* scratch = nullptr;
         unsigned long long* d_kept = nullptr;
         unsigned long long kept = 0;
-        CU(cudaMalloc(&scratch, (size_t)L.plane * sizeof(int)));
-        CU(cudaMalloc(&d_kept, sizeof(unsigned long long)));
+        CU(dmalloc(&scratch, (size_t)L.plane * sizeof(int)));
+        CU(dmalloc(&d_kept, sizeof(unsigned long long)));
         CU(cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long), stream));
         agg_count_kernel<T><<<pg, 256, 0, stream>>>(L);
         agg_prune_kernel<T><<<pg, 256, 0, stream>>>(L, 64.0, scratch, d_kept);
         agg_commit_kernel<T><<<pg, 256, 0, stream>>>(L, scratch);
         CU(cudaMemcpyAsync(&kept, d_kept, sizeof kept, cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
-        cudaFree(scratch); cudaFree(d_kept);
+        dfree(scratch); dfree(d_kept);
         if (kept == 0) {
-            cudaFree(L.label); cudaFree(L.aggD);
+            dfree(L.label); dfree(L.aggD);
             L.label = nullptr; L.aggD = nullptr;
             return HG_OK;
         }
         agg_diag_kernel<T><<<pg, 256, 0, stream>>>(L);
-        CU(cudaMalloc(&L.aggS, (size_t)L.plane * K * sizeof(double)));
+        CU(dmalloc(&L.aggS, (size_t)L.plane * K * sizeof(double)));
         CU(cudaMemsetAsync(L.aggS, 0, (size_t)L.plane * K * sizeof(double), stream));
         CU(cudaGetLastError());
         return HG_OK;
@@ -810,69 +842,48 @@ struct Solver : SolverBase {
     int build_tiles() {
         tiles_x = (pitch + FT_X - 1) / FT_X;
         tiles_y = (rows + FT_Y - 1) / FT_Y;
-        cudaFree(d_tile_active); cudaFree(d_tpart0); cudaFree(d_tpart1);
+        dfree(d_tile_active); dfree(d_tpart0); dfree(d_tpart1);
         d_tile_active = nullptr; d_tpart0 = d_tpart1 = nullptr;
-        CU(cudaMalloc(&d_tile_active, ntiles()));
-        CU(cudaMalloc(&d_tpart0, (size_t)ntiles() * K * sizeof(double)));
-        CU(cudaMalloc(&d_tpart1, (size_t)ntiles() * K * sizeof(double)));
+        CU(dmalloc(&d_tile_active, ntiles()));
+        CU(dmalloc(&d_tpart0, (size_t)ntiles() * K * sizeof(double)));
+        CU(dmalloc(&d_tpart1, (size_t)ntiles() * K * sizeof(double)));
         // inactive tiles never write their partial sums: they must read as zero
         CU(cudaMemsetAsync(d_tpart0, 0, (size_t)ntiles() * K * sizeof(double), stream));
         CU(cudaMemsetAsync(d_tpart1, 0, (size_t)ntiles() * K * sizeof(double), stream));
-        cudaFree(d_down_active); cudaFree(d_code); cudaFree(d_lpart);
+        dfree(d_down_active); dfree(d_code); dfree(d_lpart);
         d_down_active = d_code = nullptr; d_lpart = nullptr;
-        CU(cudaMalloc(&d_down_active, ntiles()));
-        CU(cudaMalloc(&d_code, plane));
-        CU(cudaMalloc(&d_lpart, (size_t)n_lap() * K * sizeof(double)));
+        CU(dmalloc(&d_down_active, ntiles()));
+        CU(dmalloc(&d_code, plane));
+        CU(dmalloc(&d_lpart, (size_t)n_lap() * K * sizeof(double)));
         CU(cudaMemsetAsync(d_lpart, 0, (size_t)n_lap() * K * sizeof(double), stream));
         tile_activity_kernel<<<tile_grid(), 256, 0, stream>>>(d_flags, rows, cols, pitch, 0, d_tile_active);
         tile_activity_kernel<<<tile_grid(), 256, 0, stream>>>(d_flags, rows, cols, pitch, 1, d_down_active);
         opcode_kernel<T><<<dim3((pitch + 255) / 256, rows), 256, 0, stream>>>(grid(), d_code);
         sl_ns = (pitch + SL_OUT - 1) / SL_OUT;
         sl_nt = (rows + SL_R - 1) / SL_R;
-        cudaFree(d_sl_up); cudaFree(d_sl_down); cudaFree(d_spart);
+        dfree(d_sl_up); dfree(d_sl_down); dfree(d_spart);
         d_sl_up = d_sl_down = nullptr; d_spart = nullptr;
-        CU(cudaMalloc(&d_sl_up, (size_t)sl_ns * sl_nt));
-        CU(cudaMalloc(&d_sl_down, (size_t)sl_ns * sl_nt));
-        CU(cudaMalloc(&d_spart, (size_t)sl_ns * sl_nt * K * sizeof(double)));
+        CU(dmalloc(&d_sl_up, (size_t)sl_ns * sl_nt));
+        CU(dmalloc(&d_sl_down, (size_t)sl_ns * sl_nt));
+        CU(dmalloc(&d_spart, (size_t)sl_ns * sl_nt * K * sizeof(double)));
         CU(cudaMemsetAsync(d_spart, 0, (size_t)sl_ns * sl_nt * K * sizeof(double), stream));
-        cudaFree(d_spart2);
+        dfree(d_spart2);
         d_spart2 = nullptr;
-        CU(cudaMalloc(&d_spart2, (size_t)sl_ns * sl_nt * K * sizeof(double)));
+        CU(dmalloc(&d_spart2, (size_t)sl_ns * sl_nt * K * sizeof(double)));
         CU(cudaMemsetAsync(d_spart2, 0, (size_t)sl_ns * sl_nt * K * sizeof(double), stream));
         sl_activity_kernel<<<dim3(sl_ns, sl_nt), 256, 0, stream>>>(d_flags, d_code, rows, cols, pitch, 0, sl_ns, d_sl_up);
         sl_activity_kernel<<<dim3(sl_ns, sl_nt), 256, 0, stream>>>(d_flags, d_code, rows, cols, pitch, 1, sl_ns, d_sl_down);
-        {   // task lists: [down lean | down general | up lean | up general], in row-major chunk order
+        {   // task lists: [down lean | down general | up lean | up general], in row-major chunk order, compacted on the
+            // device; the counts come back with the other counters at the end of hg_setup (finish_task_lists)
             const int n = sl_ns * sl_nt;
-            std::vector<uint8_t> hu(n), hd(n);
-            CU(cudaMemcpyAsync(hu.data(), d_sl_up, n, cudaMemcpyDeviceToHost, stream));
-            CU(cudaMemcpyAsync(hd.data(), d_sl_down, n, cudaMemcpyDeviceToHost, stream));
-            CU(cudaStreamSynchronize(stream));
-            std::vector<int> lists;
-            lists.reserve(2 * n);
-            int* cnt[4] = {&sl_n_down_lean, &sl_n_down_gen, &sl_n_up_lean, &sl_n_up_gen};
-            for (int which = 0; which < 4; ++which) {
-                const std::vector<uint8_t>& a = which < 2 ? hd : hu;
-                const uint8_t want = (which & 1) ? 2 : 1;
-                sl_off[which] = (int)lists.size();
-                // a down task is a boundary task if its rows 64 t - 3 .. 64 t + 66 touch a ghost band
-                auto boundary = [&](int e) {
-                    const int t = e / sl_ns;
-                    return (ghost_top > 0 && SL_R * t - 3 < ghost_top) || (ghost_bottom > 0 && SL_R * t + SL_R + 2 >= rows - ghost_bottom);
-                };
-                const bool split = overlap && world > 1 && which < 2;
-                for (int e = 0; e < n; ++e)
-                    if (a[e] == want && !(split && boundary(e))) lists.push_back(e);
-                if (which < 2) sl_n_int[which] = (int)lists.size() - sl_off[which];
-                if (split)
-                    for (int e = 0; e < n; ++e)
-                        if (a[e] == want && boundary(e)) lists.push_back(e);
-                *cnt[which] = (int)lists.size() - sl_off[which];
-            }
-            cudaFree(d_sl_tasks);
+            dfree(d_sl_tasks);
             d_sl_tasks = nullptr;
-            CU(cudaMalloc(&d_sl_tasks, std::max<size_t>(1, lists.size()) * sizeof(int)));
-            if (!lists.empty()) CU(cudaMemcpyAsync(d_sl_tasks, lists.data(), lists.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
-            CU(cudaStreamSynchronize(stream));
+            CU(dmalloc(&d_sl_tasks, (size_t)4 * n * sizeof(int)));
+            if (!d_task_counts) CU(dmalloc(&d_task_counts, 8 * sizeof(int)));
+            const int split = overlap && world > 1;
+            sl_task_lists_kernel<<<4, 1024, 0, stream>>>(d_sl_up, d_sl_down, n, sl_ns, rows, ghost_top, ghost_bottom, split, d_sl_tasks, d_task_counts);
+            for (int which = 0; which < 4; ++which) sl_off[which] = which * n;
+            task_counts_pending = true;
         }
         CU(cudaFuncSetAttribute(mg_down0_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, DOWN_H, false>)));
         CU(cudaFuncSetAttribute(mg_down0_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegionSmem<T, DOWN_H, true>)));
@@ -895,7 +906,7 @@ struct Solver : SolverBase {
         HGTRY(set_fused_attrs<1>()); HGTRY(set_fused_attrs<2>()); HGTRY(set_fused_attrs<3>()); HGTRY(set_fused_attrs<4>());
         HGTRY(build_tiles());
         if (!d_z) {
-            CU(cudaMalloc(&d_z, (size_t)plane * K * sizeof(T)));
+            CU(dmalloc(&d_z, (size_t)plane * K * sizeof(T)));
             CU(cudaMemsetAsync(d_z, 0, (size_t)plane * K * sizeof(T), stream));
         }
         int r = rows, c = cols, level = 0;
@@ -1111,10 +1122,10 @@ struct Solver : SolverBase {
     bool fused_cg() const { return use_mg() && stream_lap() && world == 1 && !coarse.empty() && generic_nu == 0 && !no_fuse; }
     int ensure_fused_buffers() {
         const size_t bytes = (size_t)plane * K * sizeof(T);
-        if (!d_p2) { CU(cudaMalloc(&d_p2, bytes)); CU(cudaMemsetAsync(d_p2, 0, bytes, stream)); }
-        if (!d_r2) { CU(cudaMalloc(&d_r2, bytes)); CU(cudaMemsetAsync(d_r2, 0, bytes, stream)); }
+        if (!d_p2) { CU(dmalloc(&d_p2, bytes)); CU(cudaMemsetAsync(d_p2, 0, bytes, stream)); }
+        if (!d_r2) { CU(dmalloc(&d_r2, bytes)); CU(cudaMemsetAsync(d_r2, 0, bytes, stream)); }
         if (!d_spart3) {
-            CU(cudaMalloc(&d_spart3, (size_t)sl_ns * sl_nt * K * sizeof(double)));
+            CU(dmalloc(&d_spart3, (size_t)sl_ns * sl_nt * K * sizeof(double)));
             CU(cudaMemsetAsync(d_spart3, 0, (size_t)sl_ns * sl_nt * K * sizeof(double), stream));
         }
         CU(cudaFuncSetAttribute(sl_down_kernel<T, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SL_WPB * SL_RING * 128 * sizeof(T))));
@@ -1213,7 +1224,7 @@ struct Solver : SolverBase {
         if (!is_setup) return fail(HG_ERR_INVALID, "hg_precond_apply: hg_setup has not been called");
         HGTRY(stage(0, r));
         const size_t bytes = (size_t)rows * cols * K * sizeof(double);
-        if (!d_out) CU(cudaMalloc(&d_out, bytes));
+        if (!d_out) CU(dmalloc(&d_out, bytes));
         dim3 pg((pitch + 255) / 256, rows);
         import_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_stage[0], d_r);
         mask_hard_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_r);
@@ -1250,6 +1261,7 @@ struct Solver : SolverBase {
         CU(cudaMemcpyAsync(counts, d_counts, sizeof counts, cudaMemcpyDeviceToHost, stream));
         CU(cudaEventRecord(ev1, stream));
         HGTRY(sync_watchful());
+        HGTRY(finish_task_lists());
         CU(cudaGetLastError());
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, ev0, ev1));
@@ -1276,7 +1288,7 @@ struct Solver : SolverBase {
     int stage(int slot, const double* host) {
         const size_t bytes = (size_t)rows * cols * K * sizeof(double);
         if (!host) return HG_OK;
-        if (!d_stage[slot]) CU(cudaMalloc(&d_stage[slot], bytes));
+        if (!d_stage[slot]) CU(dmalloc(&d_stage[slot], bytes));
         CU(cudaMemcpyAsync(d_stage[slot], host, bytes, cudaMemcpyHostToDevice, stream));
         return HG_OK;
     }
@@ -1320,7 +1332,7 @@ struct Solver : SolverBase {
         if (!x || !y) return fail(HG_ERR_INVALID, "hg_apply: NULL buffer");
         HGTRY(stage(0, x));
         const size_t bytes = (size_t)rows * cols * K * sizeof(double);
-        if (!d_out) CU(cudaMalloc(&d_out, bytes));
+        if (!d_out) CU(dmalloc(&d_out, bytes));
         dim3 pg((pitch + 255) / 256, rows);
         import_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_stage[0], d_p);
         CU(cudaMemsetAsync(d_q, 0, (size_t)plane * K * sizeof(T), stream));
@@ -1545,7 +1557,7 @@ struct Solver : SolverBase {
         const int nb_res = pg.x * pg.y;
         const size_t vbytes = (size_t)plane * K * sizeof(T);
         if (!d_z) {
-            CU(cudaMalloc(&d_z, vbytes));
+            CU(dmalloc(&d_z, vbytes));
             CU(cudaMemsetAsync(d_z, 0, vbytes, stream));
         }
         CgState init;
@@ -1715,13 +1727,11 @@ struct Solver : SolverBase {
         return HG_OK;
     }
 
-    uint8_t* d_u8 = nullptr;
-
     int upload_u8(const uint8_t* vals, hg_stats* st) override {
         if (!is_setup) return fail(HG_ERR_INVALID, "hg_solve_u8: hg_setup has not been called");
         if (!vals) return fail(HG_ERR_INVALID, "hg_solve_u8: NULL values");
         const size_t bytes = (size_t)rows * cols * K;
-        if (!d_u8) CU(cudaMalloc(&d_u8, bytes));
+        uint8_t* d_u8 = d_raw;       // (allocated by hg_set_flags: rows * cols * K bytes)
         CU(cudaEventRecord(ev0, stream));
         CU(cudaMemcpyAsync(d_u8, vals, bytes, cudaMemcpyHostToDevice, stream));
         dim3 pg((pitch + 255) / 256, rows);
@@ -1740,7 +1750,7 @@ struct Solver : SolverBase {
     int download_u8(uint8_t* out, hg_stats* st) override {
         if (!out) return fail(HG_ERR_INVALID, "hg_solve_u8: NULL output");
         const size_t bytes = (size_t)rows * cols * K;
-        if (!d_u8) CU(cudaMalloc(&d_u8, bytes));
+        uint8_t* d_u8 = d_raw;
         CU(cudaEventRecord(ev0, stream));
         dim3 pg((pitch + 255) / 256, rows);
         export_u8_kernel<T><<<pg, 256, 0, stream>>>(grid(), d_xm, d_u8);
@@ -1765,7 +1775,7 @@ struct Solver : SolverBase {
     int download(double* x, hg_stats* st) override {
         if (!x) return fail(HG_ERR_INVALID, "hg_download: NULL buffer");
         const size_t bytes = (size_t)rows * cols * K * sizeof(double);
-        if (!d_out) CU(cudaMalloc(&d_out, bytes));
+        if (!d_out) CU(dmalloc(&d_out, bytes));
         CU(cudaEventRecord(ev0, stream));
         dim3 pg((pitch + 255) / 256, rows);
         export_kernel<T, double><<<pg, 256, 0, stream>>>(grid(), d_xm, d_out);
@@ -1814,6 +1824,16 @@ extern "C" {
 int hg_version(void) { return HGRID_VERSION; }
 
 const char* hg_last_error(void) { return g_err.c_str(); }
+
+int hg_trim_memory(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return HG_OK; }
+    cudaMemPool_t pool = nullptr;
+    CU(cudaDeviceGetDefaultMemPool(&pool, dev));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemPoolTrimTo(pool, 0));
+    return HG_OK;
+}
 
 int hg_device_count(void) {
     int n = 0;

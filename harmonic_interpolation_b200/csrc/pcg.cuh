@@ -99,6 +99,20 @@ __global__ void cg_alpha_kernel(CgState* st, const double* __restrict__ part_pq,
 
 #define VEC_THREADS 256
 
+// caller's rows x cols flag bytes -> the pitch-padded plane: padding columns are hard, edge bits that point outside the grid are dropped
+__global__ void __launch_bounds__(256)
+pad_flags_kernel(const uint8_t* __restrict__ raw, uint8_t* __restrict__ flags, int rows, int cols, int pitch) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= pitch) return;
+    unsigned f = HG_FLAG_HARD;
+    if (j < cols) {
+        f = raw[(long long)i * cols + j];
+        if (i == rows - 1) f &= ~(unsigned)(HG_FLAG_CUT_DOWN | HG_FLAG_PEN_DOWN);
+        if (j == cols - 1) f &= ~(unsigned)(HG_FLAG_CUT_RIGHT | HG_FLAG_PEN_RIGHT);
+    }
+    flags[(long long)i * pitch + j] = (uint8_t)f;
+}
+
 // ---- generic (any preconditioner) CG kernels ----------------------------------------------------
 // convergence check right after the x / r update, so that the preconditioner launches that follow
 // turn into no-ops once the tolerance is met

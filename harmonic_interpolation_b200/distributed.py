@@ -54,6 +54,8 @@ def exchange_bands(first_band, last_band, rank, world, dist, device=None):
 
 def with_ghost_bands(owned, above, below):
     parts = [p for p in (above, owned, below) if p is not None]
+    if len(parts) == 1:
+        return np.ascontiguousarray(owned)           # (no copy: a 16384^2 flag plane is a quarter of a GB)
     return np.ascontiguousarray(np.concatenate(parts, axis=0))
 
 

@@ -39,16 +39,29 @@ def accept_relres(precision):
 
 
 def encode_flags(rows, cols, hard=None, soft=None, cut_down=None, cut_right=None, pen_down=None, pen_right=None):
-    """Boolean (rows, cols) planes -> one flag byte per pixel (include/hgrid.h)."""
-    f = np.zeros((rows, cols), np.uint8)
+    """Boolean (rows, cols) planes -> one flag byte per pixel (include/hgrid.h).  A few vectorised passes over the
+    planes that are given (a 16384^2 hard-only mask costs one copy)."""
+    f = None
+    tmp = None
     for plane, bit in ((hard, C.FLAG_HARD), (cut_down, C.FLAG_CUT_DOWN), (cut_right, C.FLAG_CUT_RIGHT),
                        (pen_down, C.FLAG_PEN_DOWN), (pen_right, C.FLAG_PEN_RIGHT), (soft, C.FLAG_SOFT)):
-        if plane is not None:
-            plane = np.asarray(plane, dtype=bool)
-            assert plane.shape == (rows, cols)
-            f |= plane.astype(np.uint8) * np.uint8(bit)
-    # hard wins over soft at the same pixel (recovery.py:1286-1290)
-    f[(f & C.FLAG_HARD) != 0] &= np.uint8(~C.FLAG_SOFT & 0xFF)
+        if plane is None:
+            continue
+        plane = np.ascontiguousarray(plane, dtype=bool)
+        assert plane.shape == (rows, cols)
+        v = plane.view(np.uint8)                      # 0 / 1 bytes
+        shift = bit.bit_length() - 1
+        if f is None:
+            f = np.left_shift(v, shift) if shift else v.copy()
+        else:
+            tmp = np.left_shift(v, shift, out=tmp)
+            np.bitwise_or(f, tmp, out=f)
+    if f is None:
+        return np.zeros((rows, cols), np.uint8)
+    if hard is not None and soft is not None:
+        # hard wins over soft at the same pixel (recovery.py:1286-1290)
+        tmp = np.left_shift(np.bitwise_and(f, C.FLAG_HARD, out=tmp), C.FLAG_SOFT.bit_length() - 1, out=tmp)
+        np.bitwise_and(f, np.invert(tmp, out=tmp), out=f)
     return f
 
 

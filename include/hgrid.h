@@ -104,6 +104,9 @@ int hg_device_count(void);
  * / gen_grid_laplacian2_with_boundary_reflection + L.T*L (recovery.py:349-500, 911). */
 int hg_create(int rows, int cols, int channels, int op, int precision, hg_handle* out);
 int hg_destroy(hg_handle h);
+/* Solvers take their device memory from the device's stream-ordered pool and hg_destroy returns it to the POOL, not to the
+ * driver (mapping / unmapping tens of GB costs more than a solve); hg_trim_memory() releases what the pool holds. */
+int hg_trim_memory(void);
 
 /* rows*cols flag bytes.  Replaces the sparse constraint matrices of gen_constraint_system
  * (recovery.py:504-573) and the cut-edge mask (recovery.py:309-319). */
