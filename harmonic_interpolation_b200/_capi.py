@@ -16,14 +16,15 @@ EDGES_REFERENCE, EDGES_UNIFORM = 0, 1
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_UNREFERENCED, ERR_EMPTY_ROWS = -1, -2, -3, -4, -5
-ERR_NOT_CONVERGED, ERR_BREAKDOWN, ERR_NOMEM, ERR_COMM = -6, -7, -8, -9
+ERR_NOT_CONVERGED, ERR_BREAKDOWN, ERR_NOMEM, ERR_COMM, ERR_SINGULAR = -6, -7, -8, -9, -10
 
 _dp = ctypes.POINTER(ctypes.c_double)
 
 
 class SetupInfo(ctypes.Structure):
     _fields_ = [("levels", ctypes.c_int), ("empty_rows", ctypes.c_int), ("unreferenced", ctypes.c_int),
-                ("n_free", ctypes.c_longlong), ("n_hard", ctypes.c_longlong), ("setup_ms", ctypes.c_double)]
+                ("n_free", ctypes.c_longlong), ("n_hard", ctypes.c_longlong), ("setup_ms", ctypes.c_double),
+                ("unconstrained", ctypes.c_longlong)]
 
 
 class Values(ctypes.Structure):

@@ -7,6 +7,8 @@
 #include <time.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <type_traits>
@@ -72,6 +74,14 @@ struct Nccl {
     bool ok = false;
 };
 static Nccl g_nccl;
+
+// Communicators are kept for the life of the process, one per (world, rank, device): creating one costs about a second
+// (bootstrap, channel set-up on the first send / recv to every peer), which would otherwise be paid by every solver that
+// is constructed -- a one-shot solve of a 16384^2 slab takes a tenth of that.  All ranks construct their solvers in the same
+// order, so either every rank finds its communicator here or none does.  An aborted communicator leaves the cache.
+struct CommKey { int world, rank, dev; bool operator<(const CommKey& o) const { return world != o.world ? world < o.world : (rank != o.rank ? rank < o.rank : dev < o.dev); } };
+static std::map<CommKey, ncclComm_t> g_comms;
+static std::mutex g_comms_mu;
 
 static int nccl_load() {
     if (g_nccl.ok) return HG_OK;
@@ -301,7 +311,7 @@ struct Solver : SolverBase {
         dfree(d_sl_up); dfree(d_sl_down); dfree(d_spart); dfree(d_spart2); dfree(d_sl_tasks); dfree(d_task_counts);
         dfree(d_p2); dfree(d_r2); dfree(d_spart3); dfree(d_changed);
         dfree(d_gl_rows); dfree(d_gsend);
-        if (comm && g_nccl.ok) g_nccl.CommDestroy(comm);
+        // (the communicator stays in the process-wide cache)
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream2) cudaStreamDestroy(stream2);
@@ -1245,6 +1255,36 @@ struct Solver : SolverBase {
         return HG_OK;
     }
 
+    // Free pixels of connected components that no value constraint touches (pcg.cuh).  One slab cannot decide this (a
+    // component may be anchored in a neighbouring slab): not checked in slab mode.  HGRID_ALLOW_SINGULAR=1 skips the check.
+    unsigned long long n_unconstrained = 0;
+    int find_unconstrained(unsigned long long* out) {
+        *out = 0;
+        if (world > 1 || getenv("HGRID_ALLOW_SINGULAR")) return HG_OK;
+        uint8_t* anc = nullptr;
+        int* d_ch = nullptr;
+        unsigned long long* d_cnt = nullptr;
+        CU(dmalloc(&anc, (size_t)plane));
+        CU(dmalloc(&d_ch, sizeof(int)));
+        CU(dmalloc(&d_cnt, sizeof(unsigned long long)));
+        dim3 pg((pitch + 255) / 256, rows), tg((cols + ANC_T - 1) / ANC_T, (rows + ANC_T - 1) / ANC_T);
+        anchor_init_kernel<<<pg, 256, 0, stream>>>(d_flags, rows, cols, pitch, anc);
+        const int max_rounds = 2 * ((rows + cols) / ANC_T + 2) * ANC_T;     // (a serpentine component one pixel wide)
+        int changed = 1;
+        for (int r = 0; r < max_rounds && changed; ++r) {
+            CU(cudaMemsetAsync(d_ch, 0, sizeof(int), stream));
+            anchor_spread_kernel<<<tg, 256, 0, stream>>>(d_flags, rows, cols, pitch, anc, d_ch);
+            CU(cudaMemcpyAsync(&changed, d_ch, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CU(cudaStreamSynchronize(stream));
+        }
+        CU(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), stream));
+        anchor_count_kernel<<<pg, 256, 0, stream>>>(anc, rows, cols, pitch, d_cnt);
+        CU(cudaMemcpyAsync(out, d_cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        dfree(anc); dfree(d_ch); dfree(d_cnt);
+        return HG_OK;
+    }
+
     int setup(hg_setup_info* info) override {
         if (!flags_set) return fail(HG_ERR_INVALID, "hg_setup: hg_set_flags has not been called");
         CU(cudaEventRecord(ev0, stream));
@@ -1254,6 +1294,7 @@ struct Solver : SolverBase {
         domain_check_kernel<<<pg, 256, 0, stream>>>(d_flags, rows, cols, pitch, op == HG_OP_BILAPLACIAN, d_counts);
         diag_kernel<T><<<pg, 256, 0, stream>>>(grid(), op == HG_OP_BILAPLACIAN, d_dinv);
         has_pen = w_g != 0.0;   // refined below once the flag counts are known
+        HGTRY(find_unconstrained(&n_unconstrained));
         if (use_mg()) HGTRY(build_hierarchy());
         else if (use_mg25()) HGTRY(build_hierarchy25());
         else free_hierarchy();
@@ -1280,6 +1321,13 @@ struct Solver : SolverBase {
                 return fail(HG_ERR_EMPTY_ROWS, "bilaplacian: unexpected number of empty rows in the reflected Laplacian (recovery.py:493)");
             if (counts[1] != 0)
                 return fail(HG_ERR_UNREFERENCED, "bilaplacian: a pixel is referenced by no row of the reflected Laplacian (recovery.py:495)");
+        }
+        if (info) info->unconstrained = (long long)n_unconstrained;
+        if (n_unconstrained != 0) {
+            char buf[256];
+            snprintf(buf, sizeof buf, "singular system: %llu free pixels lie in connected components that no hard or soft value constraint touches "
+                                      "(the reference's direct solver fails here, recovery.py:993)", n_unconstrained);
+            return fail(HG_ERR_SINGULAR, buf);
         }
         is_setup = true;
         return HG_OK;
@@ -1392,9 +1440,21 @@ struct Solver : SolverBase {
         }
         if (rows != row_starts[rank + 1] - row_starts[rank] + gt + gb) return fail(HG_ERR_INVALID, "hg_comm_init: local rows do not match the partition");
         HGTRY(nccl_load());
-        ncclUniqueId uid;
-        memcpy(&uid, id, sizeof uid);
-        NC(g_nccl.CommInitRank(&comm, world, uid, rank));
+        int dev = 0;
+        CU(cudaGetDevice(&dev));
+        comm_key = CommKey{world, rank, dev};
+        {
+            std::lock_guard<std::mutex> lock(g_comms_mu);
+            auto it = g_comms.find(comm_key);
+            if (it != g_comms.end()) comm = it->second;
+        }
+        if (!comm) {
+            ncclUniqueId uid;
+            memcpy(&uid, id, sizeof uid);
+            NC(g_nccl.CommInitRank(&comm, world, uid, rank));
+            std::lock_guard<std::mutex> lock(g_comms_mu);
+            g_comms[comm_key] = comm;
+        }
         is_setup = false;
         return HG_OK;
     }
@@ -1509,7 +1569,12 @@ struct Solver : SolverBase {
     // (2) Any hard failure of a solve in slab mode aborts the communicator, which releases the peers' NCCL
     // kernels; they then fail the same way within their own timeout.  A dead handle refuses further solves.
     bool comm_dead = false;
+    CommKey comm_key = {0, 0, 0};
     void abort_comm() {
+        if (comm) {
+            std::lock_guard<std::mutex> lock(g_comms_mu);
+            g_comms.erase(comm_key);
+        }
         if (comm && g_nccl.ok) g_nccl.CommAbort(comm);
         comm = nullptr;
         comm_dead = true;

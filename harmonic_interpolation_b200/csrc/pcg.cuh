@@ -99,6 +99,77 @@ __global__ void cg_alpha_kernel(CgState* st, const double* __restrict__ part_pq,
 
 #define VEC_THREADS 256
 
+// ---- unconstrained components (setup) ---------------------------------------------------------------------------------
+// The reference's direct solver fails on a singular system (cvxopt raises ArithmeticError, recovery.py:993); an iterative
+// solver would quietly return one of the solutions.  A connected component of free pixels (connected through uncut
+// edges) whose constant is in the null space -- no soft pixel in it, no hard pixel next to it across an uncut edge -- is
+// found by spreading an "anchored" mark from the pixels that ARE tied to a value.
+// anchor byte: 2 hard, 1 free and anchored, 0 free and not (yet) anchored.
+__device__ __forceinline__ bool edge_open_up(const uint8_t* flags, long long o, int pitch, int i) { return i > 0 && !(flags[o - pitch] & HG_FLAG_CUT_DOWN); }
+__device__ __forceinline__ bool edge_open_left(const uint8_t* flags, long long o, int j) { return j > 0 && !(flags[o - 1] & HG_FLAG_CUT_RIGHT); }
+__global__ void __launch_bounds__(256)
+anchor_init_kernel(const uint8_t* __restrict__ flags, int rows, int cols, int pitch, uint8_t* __restrict__ anc) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= pitch) return;
+    const long long o = (long long)i * pitch + j;
+    const unsigned f = flags[o];
+    unsigned a = 2;
+    if (j < cols && !(f & HG_FLAG_HARD)) {
+        a = (f & HG_FLAG_SOFT) ? 1u : 0u;
+        if (edge_open_up(flags, o, pitch, i) && (flags[o - pitch] & HG_FLAG_HARD)) a = 1;
+        if (edge_open_left(flags, o, j) && (flags[o - 1] & HG_FLAG_HARD)) a = 1;
+        if (i + 1 < rows && !(f & HG_FLAG_CUT_DOWN) && (flags[o + pitch] & HG_FLAG_HARD)) a = 1;
+        if (j + 1 < cols && !(f & HG_FLAG_CUT_RIGHT) && (flags[o + 1] & HG_FLAG_HARD)) a = 1;
+    }
+    anc[o] = (uint8_t)a;
+}
+// one round: every 32 x 32 tile (+ a one-pixel halo as it stands) is iterated to its local fixed point in shared memory
+#define ANC_T 32
+__global__ void __launch_bounds__(256)
+anchor_spread_kernel(const uint8_t* __restrict__ flags, int rows, int cols, int pitch, uint8_t* __restrict__ anc, int* __restrict__ changed) {
+    __shared__ uint8_t A[ANC_T + 2][ANC_T + 2];
+    __shared__ uint8_t F[ANC_T + 2][ANC_T + 2];
+    const int i0 = blockIdx.y * ANC_T - 1, j0 = blockIdx.x * ANC_T - 1;
+    for (int e = threadIdx.x; e < (ANC_T + 2) * (ANC_T + 2); e += blockDim.x) {
+        const int li = e / (ANC_T + 2), lj = e - li * (ANC_T + 2);
+        const int i = i0 + li, j = j0 + lj;
+        const bool in = i >= 0 && i < rows && j >= 0 && j < cols;
+        A[li][lj] = in ? anc[(long long)i * pitch + j] : (uint8_t)2;
+        F[li][lj] = in ? flags[(long long)i * pitch + j] : (uint8_t)(HG_FLAG_HARD | HG_FLAG_CUT_DOWN | HG_FLAG_CUT_RIGHT);
+    }
+    __syncthreads();
+    int mine = 0;
+    for (int round = 0; round < 4 * ANC_T; ++round) {
+        int ch = 0;
+        for (int e = threadIdx.x; e < ANC_T * ANC_T; e += blockDim.x) {
+            const int li = 1 + e / ANC_T, lj = 1 + e % ANC_T;
+            if (A[li][lj] != 0) continue;
+            const unsigned f = F[li][lj];
+            bool a = false;
+            a = a || (A[li - 1][lj] == 1 && !(F[li - 1][lj] & HG_FLAG_CUT_DOWN));
+            a = a || (A[li][lj - 1] == 1 && !(F[li][lj - 1] & HG_FLAG_CUT_RIGHT));
+            a = a || (A[li + 1][lj] == 1 && !(f & HG_FLAG_CUT_DOWN));
+            a = a || (A[li][lj + 1] == 1 && !(f & HG_FLAG_CUT_RIGHT));
+            if (a) { A[li][lj] = 1; ch = 1; }
+        }
+        mine |= ch;
+        if (!__syncthreads_or(ch)) break;
+    }
+    for (int e = threadIdx.x; e < ANC_T * ANC_T; e += blockDim.x) {
+        const int li = 1 + e / ANC_T, lj = 1 + e % ANC_T;
+        const int i = i0 + li, j = j0 + lj;
+        if (i < rows && j < cols && A[li][lj] == 1) anc[(long long)i * pitch + j] = 1;
+    }
+    if (mine) *changed = 1;
+}
+__global__ void __launch_bounds__(256)
+anchor_count_kernel(const uint8_t* __restrict__ anc, int rows, int cols, int pitch, unsigned long long* __restrict__ count) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    const bool loose = j < cols && anc[(long long)i * pitch + j] == 0;
+    const unsigned b = __ballot_sync(HG_FULL, loose);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, (unsigned long long)__popc(b));
+}
+
 // caller's rows x cols flag bytes -> the pitch-padded plane: padding columns are hard, edge bits that point outside the grid are dropped
 __global__ void __launch_bounds__(256)
 pad_flags_kernel(const uint8_t* __restrict__ raw, uint8_t* __restrict__ flags, int rows, int cols, int pitch) {

@@ -576,3 +576,51 @@ def normalize_to_char_img(img):
     assert len(img.shape) in (2, 3)
     lo, hi = img.min(), img.max()
     return np.asarray((255. * ((img - lo) / (hi - lo))).clip(0, 255).round(), dtype=np.uint8)
+
+
+def test_solve_grid_linear_simpleN(solve_grid_linear_simpleN):
+    """The reference's self-test (recovery.py:2020-2077, run by `python3 recovery.py`, README.md:5-6): a 250 x 250 thin-plate
+    solve with a cut-out square, hard / soft / per-equation-soft / mixed constraints, the two 1e-7 self-consistency asserts,
+    three PNGs written into the working directory."""
+    from PIL import Image
+    rows = cols = 250
+    br0, br1 = 100, 150
+    bc0, bc1 = br0, br1
+    K = 1
+    value_constraints = [
+        (0, 0, [br0 * 2.] * K), (rows - 1, 0, [0.] * K), (0, cols - 1, [0.] * K), (rows - 1, cols - 1, [0.] * K),
+        (br0, bc0, [br0] * K), (br1 - 1, bc0, [br0] * K), (br0, bc1 - 1, [br0] * K), (br1 - 1, bc1 - 1, [br0] * K)]
+    mask = np.zeros((rows, cols), dtype=bool)
+    mask[br0:br1, bc0:bc1] = True
+    cut_edges = cut_edges_from_mask(mask)
+
+    sol_hard = solve_grid_linear_simpleN(rows, cols, value_constraints_hard=value_constraints, cut_edges=cut_edges, bilaplacian=True)
+    sol_soft = solve_grid_linear_simpleN(rows, cols, value_constraints_soft=value_constraints, w_lsq=1e3, cut_edges=cut_edges, bilaplacian=True)
+    sol_soft2 = solve_grid_linear_simpleN(rows, cols, value_constraints_soft=value_constraints, w_lsq=[1e3] * len(value_constraints),
+                                          cut_edges=cut_edges, bilaplacian=True)
+    assert abs(sol_soft2 - sol_soft).max() < 1e-7
+    mid = [((br0 + br1) // 2, (bc0 + bc1) // 2, [.5 * br0] * K)]
+    sol_mixed = solve_grid_linear_simpleN(rows, cols, value_constraints_hard=value_constraints, value_constraints_soft=mid, w_lsq=1e3,
+                                          cut_edges=cut_edges, bilaplacian=True)
+    sol_mixed2 = solve_grid_linear_simpleN(rows, cols, value_constraints_hard=value_constraints, value_constraints_soft=mid, w_lsq=[1e3] * 1,
+                                           cut_edges=cut_edges, bilaplacian=True)
+    assert abs(sol_mixed2 - sol_mixed).max() < 1e-7
+
+    Image.fromarray(normalize_to_char_img(sol_hard)).save('sol_hard.png')
+    Image.fromarray(normalize_to_char_img(sol_hard)).save('sol_soft.png')       # (sic: recovery.py:2072 saves sol_hard twice)
+    Image.fromarray(normalize_to_char_img(sol_mixed)).save('sol_mixed.png')
+    print('[Saved "sol_soft.png".]')
+    print('[Saved "sol_hard.png".]')
+    print('[Saved "sol_mixed.png".]')
+    return sol_hard, sol_soft, sol_mixed
+
+
+def main():
+    """recovery.py:2096-2102: `python3 recovery.py` runs the self-test and exits."""
+    import sys
+    test_solve_grid_linear_simpleN(solve_grid_linear_simple3)
+    sys.exit(0)
+
+
+if __name__ == '__main__':
+    main()

@@ -111,6 +111,9 @@ class GridSolver:
         if code in (C.ERR_UNREFERENCED, C.ERR_EMPTY_ROWS):
             # the reference raises AssertionError here (recovery.py:493, 495)
             raise AssertionError(C.last_error())
+        if code == C.ERR_SINGULAR:
+            # cvxopt.cholmod raises ArithmeticError on the singular system (recovery.py:993)
+            raise ArithmeticError(C.last_error())
         C.check(code)
         return info
 

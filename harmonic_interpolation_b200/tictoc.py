@@ -32,3 +32,11 @@ def tictoc(msg=None):
         yield
     finally:
         toc()
+
+
+def tictoc_dec(func):
+    """tictoc.py:28-35: decorator that wraps every call of `func` in tictoc(func.__name__)."""
+    def wrapped(*args, **kwargs):
+        with tictoc(func.__name__):
+            return func(*args, **kwargs)
+    return wrapped

@@ -60,7 +60,9 @@ typedef enum {
     HG_ERR_NOT_CONVERGED = -6, /* maxiter reached (the reference asserts info == 0, recovery.py:972) */
     HG_ERR_BREAKDOWN = -7,     /* NaN / non-positive curvature: singular or under-constrained system */
     HG_ERR_NOMEM = -8,
-    HG_ERR_COMM = -9           /* slab mode: NCCL failure or a peer that stopped; the communicator is aborted */
+    HG_ERR_COMM = -9,          /* slab mode: NCCL failure or a peer that stopped; the communicator is aborted */
+    HG_ERR_SINGULAR = -10      /* a connected component of free pixels carries no value constraint: the reference's
+                                  direct solve raises ArithmeticError there (cvxopt.cholmod, recovery.py:993)          */
 } hg_status;
 
 typedef struct {
@@ -70,6 +72,7 @@ typedef struct {
     long long n_free;    /* free (unknown) pixels                          */
     long long n_hard;
     double setup_ms;
+    long long unconstrained; /* free pixels in components without any value constraint (HG_ERR_SINGULAR if != 0) */
 } hg_setup_info;
 
 /* host value arrays of one solve; each is (rows, cols, K) float64 or NULL (= zeros) */

@@ -283,3 +283,55 @@ def test_analytic_large_grid():
     assert s.last_stats["relres"] <= 1e-6
     assert np.abs(out - 0.625).max() < 1e-5
     s.close()
+
+
+def test_unconstrained_component_raises(monkeypatch):
+    """cvxopt.cholmod raises ArithmeticError on the singular system of a connected component that no value
+    constraint touches (recovery.py:993).  hg_setup finds such components by spreading an `anchored` mark over uncut edges."""
+    rows, cols = 90, 120
+    block = np.zeros((rows, cols), bool)
+    block[30:50, 40:70] = True
+    cd, cr = R.cut_planes_from_mask(block)
+    hard = np.zeros((rows, cols), bool)
+    hard[0, 0] = True
+    for bilap in (False, True):
+        s = S.GridSolver(rows, cols, 1, bilap, "fp64")
+        with pytest.raises(ArithmeticError):
+            s.set_pattern(S.encode_flags(rows, cols, hard=hard, cut_down=cd, cut_right=cr))
+        assert s.info.unconstrained == 20 * 30
+        # a soft pixel inside the cut-off block, or a hard one, makes the system regular
+        soft = np.zeros((rows, cols), bool); soft[40, 50] = True
+        s.set_pattern(S.encode_flags(rows, cols, hard=hard, soft=soft, cut_down=cd, cut_right=cr), None, 2.0)
+        h2 = hard.copy(); h2[35, 45] = True
+        s.set_pattern(S.encode_flags(rows, cols, hard=h2, cut_down=cd, cut_right=cr))
+        assert s.info.unconstrained == 0
+        s.close()
+    # no constraint at all
+    with pytest.raises(ArithmeticError):
+        S.GridSolver(20, 30, 1, False, "fp64").set_pattern(np.zeros((20, 30), np.uint8))
+    # a serpentine corridor one pixel wide, anchored only at its far end: many rounds of spreading, no false alarm
+    n = 130
+    free = np.zeros((n, n), bool)
+    for k in range(0, n, 4):
+        free[k, :] = True
+        free[k:k + 4, (n - 1) if (k // 4) % 2 == 0 else 0] = True
+    free = free[:n, :n]
+    hard = ~free
+    hard[0, 0] = False
+    cdp = np.zeros((n, n), bool); crp = np.zeros((n, n), bool)
+    # hard pixels would anchor the corridor everywhere: cut every edge between free and hard pixels, keep one hard pixel joined at the end
+    cdp[:-1] = free[:-1] != free[1:]; crp[:, :-1] = free[:, :-1] != free[:, 1:]
+    last = np.argwhere(free)[-1]
+    s = S.GridSolver(n, n, 1, False, "fp64")
+    with pytest.raises(ArithmeticError):
+        s.set_pattern(S.encode_flags(n, n, hard=~free, cut_down=cdp, cut_right=crp))
+    soft = np.zeros((n, n), bool); soft[last[0], last[1]] = True
+    s.set_pattern(S.encode_flags(n, n, hard=~free, soft=soft, cut_down=cdp, cut_right=crp), None, 1.0)
+    assert s.info.unconstrained == 0
+    x = s.solve(soft_vals=np.full((n, n, 1), 3.0))
+    assert np.abs(x[free] - 3.0).max() < 1e-8            # the harmonic function with one soft pin is the constant
+    s.close()
+    monkeypatch.setenv("HGRID_ALLOW_SINGULAR", "1")
+    s = S.GridSolver(20, 30, 1, False, "fp64")
+    s.set_pattern(np.zeros((20, 30), np.uint8))
+    s.close()

@@ -92,3 +92,44 @@ def test_constraint_array_forms_match_tuple_forms():
     a = R._cut_planes(rows, cols, edges); b = R._cut_planes(rows, cols, arr); c = R._cut_planes(rows, cols, planes)
     for x in (b, c):
         assert (a[0] == x[0]).all() and (a[1] == x[1]).all() and a[2] == x[2]
+
+
+def test_tint_functions_host_logic_against_the_reference(monkeypatch):
+    """highlighting.py:139-213, 361-464: crop / buffer / grow / rim / constraint sets / blending of the drop-in, with the CPU
+    oracle standing in for the GPU solve, against outputs of the unmodified reference (tests/golden/reference_highlighting.npz)."""
+    import contextlib
+    import io
+
+    import highlighting_cases as hc
+    from harmonic_interpolation_b200 import highlighting as H
+    from oracle import grid_oracle as go
+
+    def oracle_solve(rows, cols, value_constraints=None, bilaplacian=False, **kw):
+        mask, values = value_constraints
+        vc = [(int(i), int(j), float(values[i, j])) for i, j in zip(*np.nonzero(mask))]
+        return go.solve_grid_linear(rows, cols, value_constraints=vc, bilaplacian=bilaplacian)
+
+    monkeypatch.setattr(R, "solve_grid_linear", oracle_solve)
+    for name in hc.NAMES:
+        case = hc.load(name)
+        with contextlib.redirect_stdout(io.StringIO()):
+            got = hc.run(H, case)
+        diff = np.abs(got.astype(int) - case["out"].astype(int))
+        assert diff.max() <= 1 and (diff > 0).mean() < 1e-3, (name, diff.max())
+
+
+def test_tictoc_dec_and_nesting(capsys):
+    """tictoc.py:5-35: '+' * depth on entry, '-' * depth on exit, the decorator names the function."""
+    from harmonic_interpolation_b200 import tictoc as T
+
+    @T.tictoc_dec
+    def work(a, b=2):
+        with T.tictoc("inner"):
+            pass
+        return a * b
+
+    assert work(3, b=5) == 15
+    lines = capsys.readouterr().out.splitlines()
+    assert lines[0] == "+ work" and lines[1] == "++ inner"
+    assert lines[2].startswith("-- inner ") and lines[3].startswith("- work ")
+    assert T.starts == []
