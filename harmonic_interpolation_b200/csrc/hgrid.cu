@@ -1268,12 +1268,13 @@ struct Solver : SolverBase {
         CU(dmalloc(&d_ch, sizeof(int)));
         CU(dmalloc(&d_cnt, sizeof(unsigned long long)));
         dim3 pg((pitch + 255) / 256, rows), tg((cols + ANC_T - 1) / ANC_T, (rows + ANC_T - 1) / ANC_T);
-        anchor_init_kernel<<<pg, 256, 0, stream>>>(d_flags, rows, cols, pitch, anc);
+        const int pen = w_g != 0.0 ? 1 : 0;
+        anchor_init_kernel<<<pg, 256, 0, stream>>>(d_flags, rows, cols, pitch, pen, anc);
         const int max_rounds = 2 * ((rows + cols) / ANC_T + 2) * ANC_T;     // (a serpentine component one pixel wide)
         int changed = 1;
         for (int r = 0; r < max_rounds && changed; ++r) {
             CU(cudaMemsetAsync(d_ch, 0, sizeof(int), stream));
-            anchor_spread_kernel<<<tg, 256, 0, stream>>>(d_flags, rows, cols, pitch, anc, d_ch);
+            anchor_spread_kernel<<<tg, 256, 0, stream>>>(d_flags, rows, cols, pitch, pen, anc, d_ch);
             CU(cudaMemcpyAsync(&changed, d_ch, sizeof(int), cudaMemcpyDeviceToHost, stream));
             CU(cudaStreamSynchronize(stream));
         }

@@ -101,14 +101,16 @@ __global__ void cg_alpha_kernel(CgState* st, const double* __restrict__ part_pq,
 
 // ---- unconstrained components (setup) ---------------------------------------------------------------------------------
 // The reference's direct solver fails on a singular system (cvxopt raises ArithmeticError, recovery.py:993); an iterative
-// solver would quietly return one of the solutions.  A connected component of free pixels (connected through uncut
-// edges) whose constant is in the null space -- no soft pixel in it, no hard pixel next to it across an uncut edge -- is
-// found by spreading an "anchored" mark from the pixels that ARE tied to a value.
+// solver would quietly return one of the solutions.  A connected component of free pixels whose constant is in the null
+// space -- no soft pixel in it, no hard pixel next to it -- is found by spreading an "anchored" mark from the pixels that
+// ARE tied to a value.  Two pixels are connected if their edge is uncut OR carries a gradient (dx / dy) constraint of
+// non-zero weight: `open` = the flag bits that open a DOWN edge, shifted by one for RIGHT edges; an edge is open if it is
+// not cut or has its penalty bit set while penalties count (pen != 0).
 // anchor byte: 2 hard, 1 free and anchored, 0 free and not (yet) anchored.
-__device__ __forceinline__ bool edge_open_up(const uint8_t* flags, long long o, int pitch, int i) { return i > 0 && !(flags[o - pitch] & HG_FLAG_CUT_DOWN); }
-__device__ __forceinline__ bool edge_open_left(const uint8_t* flags, long long o, int j) { return j > 0 && !(flags[o - 1] & HG_FLAG_CUT_RIGHT); }
+__device__ __forceinline__ bool edge_open_down(unsigned f, int pen) { return !(f & HG_FLAG_CUT_DOWN) || (pen && (f & HG_FLAG_PEN_DOWN)); }
+__device__ __forceinline__ bool edge_open_right(unsigned f, int pen) { return !(f & HG_FLAG_CUT_RIGHT) || (pen && (f & HG_FLAG_PEN_RIGHT)); }
 __global__ void __launch_bounds__(256)
-anchor_init_kernel(const uint8_t* __restrict__ flags, int rows, int cols, int pitch, uint8_t* __restrict__ anc) {
+anchor_init_kernel(const uint8_t* __restrict__ flags, int rows, int cols, int pitch, int pen, uint8_t* __restrict__ anc) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
     if (j >= pitch) return;
     const long long o = (long long)i * pitch + j;
@@ -116,17 +118,17 @@ anchor_init_kernel(const uint8_t* __restrict__ flags, int rows, int cols, int pi
     unsigned a = 2;
     if (j < cols && !(f & HG_FLAG_HARD)) {
         a = (f & HG_FLAG_SOFT) ? 1u : 0u;
-        if (edge_open_up(flags, o, pitch, i) && (flags[o - pitch] & HG_FLAG_HARD)) a = 1;
-        if (edge_open_left(flags, o, j) && (flags[o - 1] & HG_FLAG_HARD)) a = 1;
-        if (i + 1 < rows && !(f & HG_FLAG_CUT_DOWN) && (flags[o + pitch] & HG_FLAG_HARD)) a = 1;
-        if (j + 1 < cols && !(f & HG_FLAG_CUT_RIGHT) && (flags[o + 1] & HG_FLAG_HARD)) a = 1;
+        if (i > 0 && (flags[o - pitch] & HG_FLAG_HARD) && edge_open_down(flags[o - pitch], pen)) a = 1;
+        if (j > 0 && (flags[o - 1] & HG_FLAG_HARD) && edge_open_right(flags[o - 1], pen)) a = 1;
+        if (i + 1 < rows && (flags[o + pitch] & HG_FLAG_HARD) && edge_open_down(f, pen)) a = 1;
+        if (j + 1 < cols && (flags[o + 1] & HG_FLAG_HARD) && edge_open_right(f, pen)) a = 1;
     }
     anc[o] = (uint8_t)a;
 }
 // one round: every 32 x 32 tile (+ a one-pixel halo as it stands) is iterated to its local fixed point in shared memory
 #define ANC_T 32
 __global__ void __launch_bounds__(256)
-anchor_spread_kernel(const uint8_t* __restrict__ flags, int rows, int cols, int pitch, uint8_t* __restrict__ anc, int* __restrict__ changed) {
+anchor_spread_kernel(const uint8_t* __restrict__ flags, int rows, int cols, int pitch, int pen, uint8_t* __restrict__ anc, int* __restrict__ changed) {
     __shared__ uint8_t A[ANC_T + 2][ANC_T + 2];
     __shared__ uint8_t F[ANC_T + 2][ANC_T + 2];
     const int i0 = blockIdx.y * ANC_T - 1, j0 = blockIdx.x * ANC_T - 1;
@@ -146,10 +148,10 @@ anchor_spread_kernel(const uint8_t* __restrict__ flags, int rows, int cols, int 
             if (A[li][lj] != 0) continue;
             const unsigned f = F[li][lj];
             bool a = false;
-            a = a || (A[li - 1][lj] == 1 && !(F[li - 1][lj] & HG_FLAG_CUT_DOWN));
-            a = a || (A[li][lj - 1] == 1 && !(F[li][lj - 1] & HG_FLAG_CUT_RIGHT));
-            a = a || (A[li + 1][lj] == 1 && !(f & HG_FLAG_CUT_DOWN));
-            a = a || (A[li][lj + 1] == 1 && !(f & HG_FLAG_CUT_RIGHT));
+            a = a || (A[li - 1][lj] == 1 && edge_open_down(F[li - 1][lj], pen));
+            a = a || (A[li][lj - 1] == 1 && edge_open_right(F[li][lj - 1], pen));
+            a = a || (A[li + 1][lj] == 1 && edge_open_down(f, pen));
+            a = a || (A[li][lj + 1] == 1 && edge_open_right(f, pen));
             if (a) { A[li][lj] = 1; ch = 1; }
         }
         mine |= ch;
