@@ -265,6 +265,15 @@ struct Solver : SolverBase {
         return HG_OK;
     }
     bool exchange_p = getenv("HGRID_EXCHANGE_P") != nullptr;
+    // Ghost-band refreshes inside the V-cycle.  What a leg computes on ghost rows is wrong only near the OUTER edge of the
+    // band, and the wrong region grows slowly: going down, b_{l+1} is wrong within floor((w + 2) / 2) + 1 rows of the edge if
+    // b_l is wrong within w (sweep 1 row, residual 1, restriction 1): 2, 3, 3, 3, 3 rows at levels 1 .. 5 against bands of
+    // 64 .. 4 rows -- no refresh is needed on the way down.  Going up a level doubles the region and the reversed sweep adds 2
+    // rows: 6 of 8 rows at level 4 without any refresh, and 14 / 30 / 62 / 126 of 16 / 32 / 64 / 128 above it -- valid, but
+    // only just.  ONE refresh of x at level 4 (8 rows of a 1/16-width plane) resets that to 6 / 14 / 30 / 62.  So a V-cycle
+    // exchanges r (level 0, 128 rows), gathers level 5 and refreshes level 4 once; HGRID_EXCHANGE_ALL=1 restores a refresh per
+    // level and leg (8 more send / recv groups per cycle).  tests/dist_check.py holds both to the single-GPU answer.
+    bool exchange_all = getenv("HGRID_EXCHANGE_ALL") != nullptr;
     // HGRID_OVERLAP=1 (slab mode; written after round 1's GPU budget was spent, NOT YET RUN on a GPU -- off by default):
     // the 128-row exchange of r at the head of the V-cycle travels on a second stream while the downward leg works
     // on the chunks that read no ghost row; the chunks next to the ghost bands follow once the rows have arrived.
@@ -1054,7 +1063,7 @@ struct Solver : SolverBase {
             } else {
                 const int Lg = HG_GATHER_LEVEL;
                 for (int l = 0; l + 1 < Lg; ++l) {       // local levels 1 .. Lg-1
-                    HGTRY(exchange_level(coarse[l], l + 1, coarse[l].b, K));
+                    if (exchange_all) HGTRY(exchange_level(coarse[l], l + 1, coarse[l].b, K));
                     coarse_down(coarse[l], coarse[l + 1], done);
                     if (l == 0) mark(HG_PH_L1_DOWN);
                 }
@@ -1069,12 +1078,12 @@ struct Solver : SolverBase {
                     CU(cudaMemcpyAsync(Ll.x + (long long)k * Ll.plane, G.x + (long long)k * G.plane + off,
                                        (size_t)Ll.plane * sizeof(T), cudaMemcpyDeviceToDevice, stream));
                 for (int l = Lg - 2; l >= 0; --l) {
-                    if (l + 2 < Lg) HGTRY(exchange_level(coarse[l + 1], l + 2, coarse[l + 1].x, K));
+                    if (exchange_all ? l + 2 < Lg : l + 2 == Lg - 1) HGTRY(exchange_level(coarse[l + 1], l + 2, coarse[l + 1].x, K));
                     if (l == 0) mark(HG_PH_COARSE);
                     coarse_up(coarse[l], coarse[l + 1], done);
                     if (l == 0) mark(HG_PH_L1_UP);
                 }
-                HGTRY(exchange_level(coarse[0], 1, coarse[0].x, K));
+                if (exchange_all) HGTRY(exchange_level(coarse[0], 1, coarse[0].x, K));
             }
         }
         Coarse<T> c0;
