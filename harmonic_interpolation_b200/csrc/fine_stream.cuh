@@ -204,12 +204,9 @@ __device__ __forceinline__ void sl_update(const SlCtx<T, SOFT>& cx, const SlRowO
 }
 
 // ---- downward leg -------------------------------------------------------------------------------------
-template <typename T, bool SOFT, bool FUSE = false>
+template <typename T, bool SOFT>
 struct SlDown {
     SlCtx<T, SOFT> cx;
-    const T* qk; T* rnk;         // FUSE: r <- r - alpha q on the way in (new r to a second buffer), partial sums of r.r
-    T alpha;
-    double rr;
     const T* rk;                 // this channel's plane of r
     Coarse<T> cl;
     T* bk; T* xk;                // this channel's planes of the next level
@@ -262,7 +259,6 @@ struct SlDown {
         z1 = z2 = z3 = r1 = s1 = s2 = zero4<T>();
         o1.cw = o2.cw = 0u; o1.fw = o2.fw = 0x01010101u;
         o0 = cx.load_op(ibeg); q0 = cx.load_op(ibeg + 1); q1 = cx.load_op(ibeg + 2); q2 = cx.load_op(ibeg + 3);
-        rr = 0.0;
         V4<T> rc = fetch(ibeg, o0);
         rq0 = fetch(ibeg + 1, q0);
         rq1 = fetch(ibeg + 2, q1);
@@ -272,23 +268,7 @@ struct SlDown {
             adv<0>(i + 1, rc);
         }
     }
-    // row i of r (FUSE: of the updated r, which the owners of the row also store)
-    __device__ __forceinline__ V4<T> fetch(int i, const SlRowOp<SOFT>& o) {
-        V4<T> v = cx.load_row(rk, i, o);
-        if (FUSE) {
-            const V4<T> qv = cx.load_row(qk, i, o);
-#pragma unroll
-            for (int p = 0; p < 4; ++p) v.v[p] -= alpha * qv.v[p];
-            if (i >= i0 && i < i0 + SL_R && owner && cx.any_free(o)) {
-                T part = T(0);
-#pragma unroll
-                for (int p = 0; p < 4; ++p) part += v.v[p] * v.v[p];
-                rr += (double)part;
-                st4(rnk + (long long)i * cx.g.pitch + cx.c0, v);
-            }
-        }
-        return v;
-    }
+    __device__ __forceinline__ V4<T> fetch(int i, const SlRowOp<SOFT>& o) { return cx.load_row(rk, i, o); }
     template <int PAR>
     __device__ __forceinline__ void adv(int i, V4<T>& rc) {
         const V4<T> rnew = fetch(i + 3, q2);
@@ -316,13 +296,11 @@ template <int N> __device__ __forceinline__ void sl_cp_wait() { asm volatile("cp
 #define SL_RING 8         // slots of the row rings (row i <-> slot i & 7)
 #define SL_PD 3           // r is requested this many rows ahead (codes two rows earlier still)
 
-template <typename T, bool TWO = false>
+template <typename T>
 struct SlLean {
     const uint8_t* code;
     const T* rk;
     T* ring;              // this lane's quad in slot 0 of the warp's ring of r rows (shared memory); slots are 128 T apart
-    const T* rk2;         // TWO: a second operand plane, fetched alongside into a second ring (same slots, same commit groups)
-    T* ring2;
     int rows, pitch, c0, i0;
     bool colin, owner;
     V4<T> Z[8];
@@ -340,16 +318,9 @@ struct SlLean {
         T* dst = ring + slot * 128;
         sl_cp16(dst, src, m != 0u);
         if (sizeof(T) == 8) sl_cp16(dst + 2, src + 2, m != 0u);
-        if (TWO) {
-            const T* src2 = rk2 + (m ? i * pitch + c0 : 0);
-            T* dst2 = ring2 + slot * 128;
-            sl_cp16(dst2, src2, m != 0u);
-            if (sizeof(T) == 8) sl_cp16(dst2 + 2, src2 + 2, m != 0u);
-        }
         sl_cp_commit();
     }
     __device__ __forceinline__ V4<T> row(int slot) const { return ld4(ring + slot * 128); }
-    __device__ __forceinline__ V4<T> row2(int slot) const { return ld4(ring2 + slot * 128); }
     __device__ __forceinline__ void init(int ibeg, int slot0) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) { Z[q] = zero4<T>(); M[q] = 0u; }
@@ -391,16 +362,9 @@ struct SlLean {
     }
 };
 
-// FUSE: the CG update r <- r - alpha q (+ partial sums of r.r) rides along: r and q arrive together, the new r
-// is written to a SECOND buffer (halo pixels are recomputed by the neighbouring warps from the old one, so
-// the update cannot be in place) and feeds the smoothing directly.
-template <typename T, bool FUSE = false>
-struct SlLeanDown : SlLean<T, FUSE> {
-    using B = SlLean<T, FUSE>;
-    T* rnk;               // FUSE: this channel's plane of the new r
-    T alpha;
-    double rr;
-    V4<T> Rn[8];          // FUSE: the new r of rows i, i - 1
+template <typename T>
+struct SlLeanDown : SlLean<T> {
+    using B = SlLean<T>;
     T* bk; T* xk;
     const uint8_t* ccode;
     int zero_x;
@@ -412,22 +376,9 @@ struct SlLeanDown : SlLean<T, FUSE> {
         constexpr int C = (5 + U) & 7, C1 = (C + 7) & 7, C2 = (C + 6) & 7, C3 = (C + 5) & 7, C4 = (C + 4) & 7;
         constexpr int PAR = (5 + U) & 1;
         const int i = ib + U;
-        V4<T> rc = B::template advance<C>(i);
-        if (FUSE) {
-            const V4<T> qv = B::row2(C);
-#pragma unroll
-            for (int p = 0; p < 4; ++p) rc.v[p] -= alpha * qv.v[p];
-            Rn[C] = rc;
-            if (i >= B::i0 && i < B::i0 + SL_R && B::owner && B::M[C]) {
-                T part = T(0);
-#pragma unroll
-                for (int p = 0; p < 4; ++p) part += rc.v[p] * rc.v[p];
-                rr += (double)part;
-                st4(rnk + (i * B::pitch + B::c0), rc);
-            }
-        }
+        const V4<T> rc = B::template advance<C>(i);
         B::template red_first<C, PAR>(rc, T(0), T(0));
-        B::template update<C1, C2, C, PAR>(FUSE ? Rn[C1] : B::row(C1));        // black pixels of row i - 1
+        B::template update<C1, C2, C, PAR>(B::row(C1));        // black pixels of row i - 1
         {   // residual at the red pixels of row i - 2
             T nA, nB;
             B::template nsum<C2, C3, C1, PAR>(nA, nB);
@@ -456,9 +407,8 @@ struct SlLeanDown : SlLean<T, FUSE> {
         }
     }
     __device__ __forceinline__ void run() {
-        rr = 0.0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { S[q] = zero4<T>(); Rn[q] = zero4<T>(); }
+        for (int q = 0; q < 8; ++q) S[q] = zero4<T>();
         B::init(B::i0 - 3, 5);
 #pragma unroll 1
         for (int ib = B::i0 - 3; ib < B::i0 + SL_R + 3; ib += 8) {
@@ -532,18 +482,10 @@ template <typename T> __device__ __forceinline__ T* sl_ring() {
 }
 
 // One warp per task (chunk) and channel; `tasks` lists the chunks of one kind (lean or general).
-// FUSE: also r_new = r - alpha q (alpha from the CG state), written to `rnew`, partial sums of r_new.r_new to part_rr.
-struct SlFuse {
-    const void* q;
-    void* rnew;
-    const CgState* st;
-    double* part_rr;
-    int nt;
-};
-template <typename T, bool SOFT, bool LEAN, bool FUSE = false>
-__global__ void __launch_bounds__(32 * SL_WPB, LEAN ? (sizeof(T) == 4 ? (FUSE ? 3 : 4) : 2) : 1)
+template <typename T, bool SOFT, bool LEAN>
+__global__ void __launch_bounds__(32 * SL_WPB, LEAN ? (sizeof(T) == 4 ? 4 : 2) : 1)
 sl_down_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict__ r, Coarse<T> cl, const int* __restrict__ tasks,
-               int ntasks, int ns, int zero_x, const int* __restrict__ done, SlFuse fu) {
+               int ntasks, int ns, int zero_x, const int* __restrict__ done) {
     if (done && *done) return;
     const int wid = blockIdx.x * SL_WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;     // warp <-> (task, channel)
     const int idx = wid / g.K, k = wid - idx * g.K;
@@ -559,14 +501,8 @@ sl_down_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict_
         wjp[q] = (T)w1d(1, J, g.cols, cl.cols);
     }
     if (LEAN) {
-        SlLeanDown<T, FUSE> f;
+        SlLeanDown<T> f;
         f.ring = sl_ring<T>();
-        if (FUSE) {
-            f.ring2 = f.ring + SL_WPB * SL_RING * 128;
-            f.rk2 = static_cast<const T*>(fu.q) + k * g.plane;
-            f.rnk = static_cast<T*>(fu.rnew) + k * g.plane;
-            f.alpha = (T)fu.st->alpha[k];
-        }
         f.code = code; f.rk = r + k * g.plane;
         f.rows = g.rows; f.pitch = g.pitch; f.i0 = t * SL_R;
         f.c0 = c0; f.colin = colin; f.owner = owner;
@@ -574,17 +510,8 @@ sl_down_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict_
         f.grows = g.rows; f.crows = cl.rows; f.ccols = cl.cols; f.cpitch = cl.pitch;
         f.wjm[0] = wjm[0]; f.wjm[1] = wjm[1]; f.wjp[0] = wjp[0]; f.wjp[1] = wjp[1];
         f.run();
-        if (FUSE) {
-            const double s2 = warp_sum(f.rr);
-            if (lane == 0) fu.part_rr[(long long)k * ((long long)ns * fu.nt) + task] = s2;
-        }
     } else {
-        SlDown<T, SOFT, FUSE> d;
-        if (FUSE) {
-            d.qk = static_cast<const T*>(fu.q) + k * g.plane;
-            d.rnk = static_cast<T*>(fu.rnew) + k * g.plane;
-            d.alpha = (T)fu.st->alpha[k];
-        }
+        SlDown<T, SOFT> d;
         d.lane = lane;
         d.cx.g = g; d.cx.code = code; d.cx.c0 = c0; d.cx.colin = colin; d.owner = owner;
         d.rk = r + k * g.plane;
@@ -593,10 +520,6 @@ sl_down_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict_
         d.i0 = t * SL_R;
         d.wjm[0] = wjm[0]; d.wjm[1] = wjm[1]; d.wjp[0] = wjp[0]; d.wjp[1] = wjp[1];
         d.run();
-        if (FUSE) {
-            const double s2 = warp_sum(d.rr);
-            if (lane == 0) fu.part_rr[(long long)k * ((long long)ns * fu.nt) + task] = s2;
-        }
     }
 }
 
@@ -831,132 +754,6 @@ sl_lap_kernel(Grid<TO> g, const uint8_t* __restrict__ code, const TX* __restrict
     f.run();
     const double sdot = warp_sum(f.acc);
     if (lane == 0) part_pq[(long long)k * ((long long)ns * nt) + task] = sdot;
-}
-
-// ---- fused CG step around the stencil: p_new = z + beta p;  x += alpha p;  q = A p_new (+ p_new.q) -------------
-// z and p arrive together through the ring pair; p_new goes to a second buffer (halo rows and columns are
-// recomputed by the neighbouring warps from the old p); x is read-modify-written by the owners only.
-// `first`: the first iteration of a CG run -- p_new = z, no x update.
-template <typename T, bool GENERAL>
-struct SlLapFused : SlLean<T, true> {
-    using B = SlLean<T, true>;
-    static constexpr int PD = 3;
-    T* pnk; T* qk; T* xk;
-    T alpha, beta;
-    int first;
-    double acc;
-    V4<T> P[8];
-
-    // row i has landed in slot `slot`: p_new into the register window; owners of the row store it and update x
-    __device__ __forceinline__ void arrive(int i, int slot, V4<T>& dst, unsigned m, bool own_row) {
-        const V4<T> zv = B::row(slot);
-        dst = zv;
-        if (!first) {
-            const V4<T> pv = B::row2(slot);
-#pragma unroll
-            for (int p = 0; p < 4; ++p) dst.v[p] = zv.v[p] + beta * pv.v[p];
-            if (own_row && B::owner && m) {
-                T* xp = xk + (i * B::pitch + B::c0);
-                V4<T> xv = ld4(xp);
-#pragma unroll
-                for (int p = 0; p < 4; ++p) xv.v[p] += alpha * pv.v[p];
-                st4(xp, xv);
-            }
-        }
-        if (own_row && B::owner && m) st4(pnk + (i * B::pitch + B::c0), dst);
-    }
-    template <int U> __device__ __forceinline__ void step(int ib) {     // ib = i0 (mod 8: 0)
-        constexpr int C = U & 7, CU = (C + 7) & 7, CD = (C + 1) & 7;
-        const int i = ib + U;
-        B::M[(C + PD + 3) & 7] = B::load_code(i + PD + 3);
-        B::request(i + 1 + PD, (C + 1 + PD) & 7, B::M[(C + 1 + PD) & 7]);
-        sl_cp_wait<PD>();
-        arrive(i + 1, CD, P[CD], B::M[CD], i + 1 < B::i0 + SL_R);
-        const unsigned m = B::M[C];
-        const T lf0 = sl_up1(P[C].v[3]), rt3 = sl_dn1(P[C].v[0]);
-        if (B::owner && m) {
-            V4<T> out;
-            T part = T(0);
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                const unsigned cb = (m >> (8 * p)) & 0xffu;
-                const T lf = p == 0 ? lf0 : P[C].v[p - 1], rt = p == 3 ? rt3 : P[C].v[p + 1];
-                T v;
-                if (!GENERAL || cb == 0xAAu || cb == 0u) {
-                    v = cb ? P[C].v[p] - T(0.25) * ((P[CU].v[p] + P[CD].v[p]) + (lf + rt)) : T(0);
-                } else {
-                    T wu, wd, wl, wr;
-                    decode(cb, wu, wd, wl, wr);
-                    v = (wu + wd + wl + wr) * P[C].v[p] - wu * P[CU].v[p] - wd * P[CD].v[p] - wl * lf - wr * rt;
-                }
-                out.v[p] = v;
-                part += P[C].v[p] * v;
-            }
-            acc += (double)part;
-            st4(qk + (i * B::pitch + B::c0), out);
-        }
-    }
-    __device__ __forceinline__ void run() {
-        acc = 0.0;
-        const int i0 = B::i0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { P[q] = zero4<T>(); B::M[q] = 0u; }
-#pragma unroll
-        for (int q = -1; q < PD + 3; ++q) B::M[q & 7] = B::load_code(i0 + q);
-#pragma unroll
-        for (int q = -1; q <= PD; ++q) B::request(i0 + q, q & 7, B::M[q & 7]);
-        sl_cp_wait<PD>();          // rows i0 - 1 and i0 have landed
-        arrive(i0 - 1, 7, P[7], B::M[7], false);
-        arrive(i0, 0, P[0], B::M[0], true);
-#pragma unroll 1
-        for (int ib = i0; ib < i0 + SL_R; ib += 8) {
-            step<0>(ib); step<1>(ib); step<2>(ib); step<3>(ib); step<4>(ib); step<5>(ib); step<6>(ib); step<7>(ib);
-        }
-        sl_cp_wait<0>();
-    }
-};
-
-template <typename T, bool GENERAL>
-__global__ void __launch_bounds__(32 * SL_WPB, sizeof(T) == 4 ? 3 : 2)
-sl_lap_fused_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict__ z, const T* __restrict__ p, T* __restrict__ pnew,
-                    T* __restrict__ x, T* __restrict__ q, const CgState* __restrict__ st, int first, const int* __restrict__ tasks,
-                    int ntasks, int ns, int nt, double* __restrict__ part_pq) {
-    if (st->done) return;
-    const int wid = blockIdx.x * SL_WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    const int idx = wid / g.K, k = wid - idx * g.K;
-    if (idx >= ntasks) return;
-    const int task = tasks[idx], t = task / ns, s = task - t * ns;
-    SlLapFused<T, GENERAL> f;
-    f.ring = sl_ring<T>();
-    f.ring2 = f.ring + SL_WPB * SL_RING * 128;
-    f.code = code; f.rk = z + k * g.plane; f.rk2 = p + k * g.plane;
-    f.pnk = pnew + k * g.plane; f.qk = q + k * g.plane; f.xk = x + k * g.plane;
-    f.alpha = (T)st->alpha[k]; f.beta = (T)st->beta[k]; f.first = first;
-    f.rows = g.rows; f.pitch = g.pitch; f.i0 = t * SL_R;
-    f.c0 = s * SL_OUT - 4 + 4 * lane;
-    f.colin = f.c0 >= 0 && f.c0 < g.pitch;
-    f.owner = lane >= 1 && lane <= 30;
-    f.run();
-    const double sdot = warp_sum(f.acc);
-    if (lane == 0) part_pq[(long long)k * ((long long)ns * nt) + task] = sdot;
-}
-
-// x += alpha p at the end of a CG run (the fused loop applies each update one iteration late); NOT gated by `done`
-template <typename T>
-__global__ void __launch_bounds__(256)
-cg_xfinal_kernel(const CgState* __restrict__ st, long long plane, int K, T* __restrict__ x, const T* __restrict__ p) {
-    const long long n4 = plane >> 2;
-    for (int k = 0; k < K; ++k) {
-        const T a = (T)st->alpha[k];
-        for (long long v = (long long)blockIdx.x * 256 + threadIdx.x; v < n4; v += (long long)gridDim.x * 256) {
-            const long long o = k * plane + (v << 2);
-            V4<T> xv = ld4(x + o);
-            const V4<T> pv = ld4(p + o);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) xv.v[c] += a * pv.v[c];
-            st4(x + o, xv);
-        }
-    }
 }
 
 }  // namespace hg

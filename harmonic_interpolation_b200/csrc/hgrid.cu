@@ -220,10 +220,6 @@ struct Solver : SolverBase {
     uint8_t *d_sl_up = nullptr, *d_sl_down = nullptr;
     double* d_spart = nullptr;
     double* d_spart2 = nullptr;        // per-chunk partial sums of p.q (streaming stencil kernel)
-    // fused CG loop: second buffers of p and r (the streaming kernels recompute halo pixels from the old vector),
-    // per-chunk partial sums of r.r
-    T *d_p2 = nullptr, *d_r2 = nullptr;
-    double* d_spart3 = nullptr;
     // Phase timing (hg_set_phase_timing, or HGRID_PHASES=1 which also prints to stderr): CUDA events on the solver's
     // stream between the launches of the MG-PCG loop; totals per phase of the last solve are kept for hg_get_phase_ms.
     bool phase_print = getenv("HGRID_PHASES") != nullptr;
@@ -281,7 +277,6 @@ struct Solver : SolverBase {
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_arrived = nullptr;
     int sl_n_int[2] = {0, 0};          // down lists (lean, general): number of interior tasks, which come first
-    bool no_fuse = getenv("HGRID_FUSE") == nullptr;      // the fused loop is opt-in (HGRID_FUSE=1): it does not pay yet
     int sl_ns = 0, sl_nt = 0;
     int* d_sl_tasks = nullptr;
     int* d_task_counts = nullptr;
@@ -318,7 +313,7 @@ struct Solver : SolverBase {
         dfree(d_tile_active); dfree(d_tpart0); dfree(d_tpart1);
         dfree(d_down_active); dfree(d_code); dfree(d_lpart);
         dfree(d_sl_up); dfree(d_sl_down); dfree(d_spart); dfree(d_spart2); dfree(d_sl_tasks); dfree(d_task_counts);
-        dfree(d_p2); dfree(d_r2); dfree(d_spart3); dfree(d_changed);
+        dfree(d_changed);
         dfree(d_gl_rows); dfree(d_gsend);
         // (the communicator stays in the process-wide cache)
         if (ev0) cudaEventDestroy(ev0);
@@ -1031,14 +1026,12 @@ struct Solver : SolverBase {
         return HG_OK;
     }
 
-    // fuse_r_old != nullptr: the downward leg also forms r = fuse_r_old - alpha q (CG update) and the convergence
-    // check runs right after it, so that the rest of the cycle turns into no-ops once the tolerance is met
-    int vcycle(T* z, T* r, const int* done, double* part_rz, const T* fuse_r_old = nullptr) {
+    int vcycle(T* z, T* r, const int* done, double* part_rz) {
         if (generic_nu > 0 && world == 1) return vcycle_generic(z, r, done);
         const Grid<T> g = grid();
         const int nl = (int)coarse.size();
         if (nl > 0) {
-            if (world > 1 && overlap && stream_legs() && !fuse_r_old) {
+            if (world > 1 && overlap && stream_legs()) {
                 CU(cudaEventRecord(ev_ready, stream));               // r is final on the owned rows
                 CU(cudaStreamWaitEvent(stream2, ev_ready, 0));
                 HGTRY(exchange(r, HG_GHOST_ROWS, stream2));
@@ -1049,10 +1042,7 @@ struct Solver : SolverBase {
                 mark(HG_PH_FINE_DOWN);
             } else {
             if (world > 1) HGTRY(exchange(r, HG_GHOST_ROWS));
-            if (fuse_r_old) {
-                launch_sl_down_fused(g, fuse_r_old, r, coarse[0], done);
-                HGTRY(stage_check(d_spart3, sl_ns * sl_nt, (long long)sl_ns * sl_nt));
-            } else if (stream_legs()) { launch_sl_down(g, r, coarse[0], done); mark(HG_PH_FINE_DOWN); }
+            if (stream_legs()) { launch_sl_down(g, r, coarse[0], done); mark(HG_PH_FINE_DOWN); }
             else if (has_pen) mg_down0_kernel<T, true><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, DOWN_H, true>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
             else if (scalar_legs) mg_down0_kernel<T, false><<<tile_grid(), FT_THREADS, sizeof(RegionSmem<T, DOWN_H, false>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
             else mg_down0v_kernel<T><<<tile_grid(), VR_THREADS, sizeof(VRegionSmem<T>), stream>>>(g, d_code, r, coarse[0], d_down_active, done);
@@ -1107,50 +1097,15 @@ struct Solver : SolverBase {
     // part 0: every task; 1: the interior tasks (front of the lists); 2: the boundary tasks (HGRID_OVERLAP)
     void launch_sl_down(const Grid<T>& g, const T* r, const Coarse<T>& c1, const int* done, int part = 0) {
         const int zx = unfused_coarse ? 1 : 0;
-        const SlFuse nf = {nullptr, nullptr, nullptr, nullptr, 0};
         const int o_l = part == 2 ? sl_n_int[0] : 0, n_l = part == 1 ? sl_n_int[0] : sl_n_down_lean - o_l;
         const int o_g = part == 2 ? sl_n_int[1] : 0, n_g = part == 1 ? sl_n_int[1] : sl_n_down_gen - o_g;
         if (n_l > 0)
-            sl_down_kernel<T, false, true><<<sl_grid(n_l), sl_block(), sl_smem(), stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[0] + o_l, n_l, sl_ns, zx, done, nf);
+            sl_down_kernel<T, false, true><<<sl_grid(n_l), sl_block(), sl_smem(), stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[0] + o_l, n_l, sl_ns, zx, done);
         if (n_g > 0) {
-            if (has_soft()) sl_down_kernel<T, true, false><<<sl_grid(n_g), sl_block(), 0, stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[1] + o_g, n_g, sl_ns, zx, done, nf);
-            else sl_down_kernel<T, false, false><<<sl_grid(n_g), sl_block(), 0, stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[1] + o_g, n_g, sl_ns, zx, done, nf);
+            if (has_soft()) sl_down_kernel<T, true, false><<<sl_grid(n_g), sl_block(), 0, stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[1] + o_g, n_g, sl_ns, zx, done);
+            else sl_down_kernel<T, false, false><<<sl_grid(n_g), sl_block(), 0, stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[1] + o_g, n_g, sl_ns, zx, done);
         }
         launches += (n_l > 0) + (n_g > 0) - (part == 2 ? 0 : 1);
-    }
-    // the same leg with the CG update fused in: r_new = r_old - alpha q (to `r_new`), partial sums of r_new.r_new
-    void launch_sl_down_fused(const Grid<T>& g, const T* r_old, T* r_new, const Coarse<T>& c1, const int* done) {
-        const SlFuse fu = {d_q, r_new, d_state, d_spart3, sl_nt};
-        if (sl_n_down_lean)
-            sl_down_kernel<T, false, true, true><<<sl_grid(sl_n_down_lean), sl_block(), 2 * sl_smem(), stream>>>(g, d_code, r_old, c1, d_sl_tasks + sl_off[0], sl_n_down_lean, sl_ns, 0, done, fu);
-        if (sl_n_down_gen)
-            sl_down_kernel<T, false, false, true><<<sl_grid(sl_n_down_gen), sl_block(), 0, stream>>>(g, d_code, r_old, c1, d_sl_tasks + sl_off[1], sl_n_down_gen, sl_ns, 0, done, fu);
-        launches += (sl_n_down_lean > 0) + (sl_n_down_gen > 0) - 1;
-    }
-    // p_new = z + beta p_old;  x += alpha p_old;  q = A p_new;  partial sums of p_new.q  -- and the scalar stage for alpha
-    int fused_lap_and_alpha(const T* z, const T* p_old, T* p_new, T* x, int first) {
-        const Grid<T> g = grid();
-        if (sl_n_up_lean)
-            sl_lap_fused_kernel<T, false><<<sl_grid(sl_n_up_lean), sl_block(), 2 * sl_smem(), stream>>>(g, d_code, z, p_old, p_new, x, d_q, d_state, first, d_sl_tasks + sl_off[2], sl_n_up_lean, sl_ns, sl_nt, d_spart2);
-        if (sl_n_up_gen)
-            sl_lap_fused_kernel<T, true><<<sl_grid(sl_n_up_gen), sl_block(), 2 * sl_smem(), stream>>>(g, d_code, z, p_old, p_new, x, d_q, d_state, first, d_sl_tasks + sl_off[3], sl_n_up_gen, sl_ns, sl_nt, d_spart2);
-        launches += (sl_n_up_lean > 0) + (sl_n_up_gen > 0);
-        return stage_alpha(d_spart2, sl_ns * sl_nt, (long long)sl_ns * sl_nt);
-    }
-    // the fused loop serves the single-GPU Laplacian + multigrid path without soft weights / penalty edges
-    bool fused_cg() const { return use_mg() && stream_lap() && world == 1 && !coarse.empty() && generic_nu == 0 && !no_fuse; }
-    int ensure_fused_buffers() {
-        const size_t bytes = (size_t)plane * K * sizeof(T);
-        if (!d_p2) { CU(dmalloc(&d_p2, bytes)); CU(cudaMemsetAsync(d_p2, 0, bytes, stream)); }
-        if (!d_r2) { CU(dmalloc(&d_r2, bytes)); CU(cudaMemsetAsync(d_r2, 0, bytes, stream)); }
-        if (!d_spart3) {
-            CU(dmalloc(&d_spart3, (size_t)sl_ns * sl_nt * K * sizeof(double)));
-            CU(cudaMemsetAsync(d_spart3, 0, (size_t)sl_ns * sl_nt * K * sizeof(double), stream));
-        }
-        CU(cudaFuncSetAttribute(sl_down_kernel<T, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SL_WPB * SL_RING * 128 * sizeof(T))));
-        CU(cudaFuncSetAttribute(sl_lap_fused_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SL_WPB * SL_RING * 128 * sizeof(T))));
-        CU(cudaFuncSetAttribute(sl_lap_fused_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SL_WPB * SL_RING * 128 * sizeof(T))));
-        return HG_OK;
     }
     void launch_sl_up(const Grid<T>& g, const T* r, T* z, const Coarse<T>& c1, int have_coarse, const int* done) {
         if (sl_n_up_lean)
@@ -1692,18 +1647,7 @@ struct Solver : SolverBase {
 
             // inner PCG on A e = r, e0 = 0 (fp32 mode) or continuing from x (fp64 mode)
             if (kRefine) CU(cudaMemsetAsync(d_x, 0, vbytes, stream));
-            const bool fuse = mg && fused_cg();
-            T* pbuf[2] = {d_p, d_p2};
-            T* rbuf[2] = {d_r, d_r2};
-            const int iter0 = host.iter;
-            int jq = 0;                 // iterations of this run enqueued so far
-            if (fuse) {
-                HGTRY(ensure_fused_buffers());
-                pbuf[1] = d_p2; rbuf[1] = d_r2;
-                HGTRY(vcycle(d_z, d_r, done, d_tpart1));
-                HGTRY(stage_beta_rz(1));
-                launches += 1;
-            } else if (mg) {
+            if (mg) {
                 HGTRY(vcycle(d_z, d_r, done, d_tpart1));
                 HGTRY(stage_beta_rz(1));
                 cg_pupdate_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(d_state, g, d_p, d_z, d_tile_active, 1);
@@ -1718,15 +1662,7 @@ struct Solver : SolverBase {
             }
             while (true) {
                 for (int s = 0; s < batch; ++s) {
-                    if (fuse) {
-                        // iteration j: p_j = z + beta p_{j-1} (and x += alpha_{j-1} p_{j-1}), q = A p_j | alpha_j |
-                        // r_j = r_{j-1} - alpha_j q inside the downward leg | check | rest of the V-cycle | beta
-                        ++jq;
-                        HGTRY(fused_lap_and_alpha(d_z, pbuf[(jq - 1) & 1], pbuf[jq & 1], e, jq == 1));
-                        HGTRY(vcycle(d_z, rbuf[jq & 1], done, d_tpart1, rbuf[(jq - 1) & 1]));
-                        HGTRY(stage_beta_rz(0));
-                        launches += 3;
-                    } else if (mg) {
+if (mg) {
                         mark(HG_PH_OTHER);
                         // (no exchange of p: its ghost rows are computed redundantly from z and the old p, and are
                         // valid next to the owned band just as the ghost rows of z are; HGRID_EXCHANGE_P=1 restores it)
@@ -1758,11 +1694,6 @@ struct Solver : SolverBase {
                 CU(cudaMemcpyAsync(&host, d_state, sizeof host, cudaMemcpyDeviceToHost, stream));
                 HGTRY(sync_watchful());
                 if (host.done) break;
-            }
-            if (fuse && host.iter > iter0 && host.done != 2) {
-                // the update of the last executed iteration J is still owed: x += alpha_J p_J (p_J sits in pbuf[J & 1])
-                cg_xfinal_kernel<T><<<vec_blocks(), 256, 0, stream>>>(d_state, plane, K, e, pbuf[(host.iter - iter0) & 1]);
-                ++launches;
             }
             if (kRefine) {
                 if (mg) axpy_master_tile_kernel<T><<<tile_grid(), FT_THREADS, 0, stream>>>(g, d_xm, d_x, d_tile_active);

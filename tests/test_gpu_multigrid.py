@@ -268,33 +268,6 @@ def test_streaming_kernels_any_channel_count(K):
         s.close()
 
 
-def test_fused_cg_loop_matches_the_separate_kernels(monkeypatch):
-    """HGRID_FUSE=1 (p-update + x-update inside the stencil kernel, r-update inside the downward leg) is the same
-    iteration: same iteration count, same answer to rounding."""
-    rows, cols, K = 333, 260, 3
-    rng = np.random.default_rng(2)
-    hard = np.kron(rng.random((rows // 16 + 1, cols // 16 + 1)) < 0.5, np.ones((16, 16), bool))[:rows, :cols]
-    hard[0, 0] = True
-    vals = rng.random((rows, cols, K))
-    res = {}
-    for fuse in (False, True):
-        if fuse:
-            monkeypatch.setenv("HGRID_FUSE", "1")
-        else:
-            monkeypatch.delenv("HGRID_FUSE", raising=False)
-        for prec in ("fp32", "fp64"):
-            s = S.GridSolver(rows, cols, K, False, prec, "multigrid")
-            s.set_pattern(S.encode_flags(rows, cols, hard=hard))
-            out = s.solve(hard_vals=vals, rtol=1e-8)
-            res[(fuse, prec)] = (out, s.last_stats["iterations"])
-            s.close()
-    for prec, tol in (("fp32", 1e-6), ("fp64", 1e-10)):
-        a, ia = res[(False, prec)]
-        b, ib = res[(True, prec)]
-        assert abs(ia - ib) <= 1, (prec, ia, ib)
-        assert np.abs(a - b).max() < tol
-
-
 @pytest.mark.parametrize("prec", ["fp64", "fp32"])
 @pytest.mark.parametrize("shape", [(700, 900), (2050, 1030), (130, 4100), (97, 61)])
 def test_streaming_coarse_legs_match_tile_legs(monkeypatch, prec, shape):
