@@ -202,13 +202,6 @@ struct Solver : SolverBase {
     std::vector<Lev25<T>> lev25;
     double* d_dense25 = nullptr;
     int mg25_sweeps = getenv("HGRID_MG25_SWEEPS") ? atoi(getenv("HGRID_MG25_SWEEPS")) : 1;
-    bool mg25_rowgs = getenv("HGRID_MG25_ROWGS") != nullptr;    // row-coloured smoother (mg25.cuh): not yet run on a GPU, opt-in
-    T* d_z2 = nullptr;                                           // level-0 half of its double buffer
-    // finest levels that get the aggregate correction (experimental, off by default: it cuts the iteration count 4x at
-    // 256^2 but does not scale -- at 2048^2 the undamped additive step on densely coupled clusters costs iterations)
-    int mg25_agg_levels = getenv("HGRID_MG25_AGG") ? atoi(getenv("HGRID_MG25_AGG")) : 0;
-    double mg25_agg_theta = getenv("HGRID_MG25_THETA") ? atof(getenv("HGRID_MG25_THETA")) : 10.0;   // strong: |a_pq| > theta * interior diagonal
-    int* d_changed = nullptr;
     // tile path (Laplacian + multigrid): activity map and per-tile partial sums
     uint8_t* d_tile_active = nullptr;
     double *d_tpart0 = nullptr, *d_tpart1 = nullptr;
@@ -313,7 +306,7 @@ struct Solver : SolverBase {
         dfree(d_tile_active); dfree(d_tpart0); dfree(d_tpart1);
         dfree(d_down_active); dfree(d_code); dfree(d_lpart);
         dfree(d_sl_up); dfree(d_sl_down); dfree(d_spart); dfree(d_spart2); dfree(d_sl_tasks); dfree(d_task_counts);
-        dfree(d_changed);
+        
         dfree(d_gl_rows); dfree(d_gsend);
         // (the communicator stays in the process-wide cache)
         if (ev0) cudaEventDestroy(ev0);
@@ -468,14 +461,12 @@ struct Solver : SolverBase {
         dfree(d_dense); dfree(d_gdense);
         d_dense = d_gdense = nullptr;
         for (size_t l = 0; l < lev25.size(); ++l) {
-            dfree(lev25[l].coef); dfree(lev25[l].label); dfree(lev25[l].aggD); dfree(lev25[l].aggS);
-            if (l > 0) { dfree(lev25[l].x); dfree(lev25[l].b); dfree(lev25[l].x2); }
+            dfree(lev25[l].coef);
+            if (l > 0) { dfree(lev25[l].x); dfree(lev25[l].b); }
         }
         lev25.clear();
         dfree(d_dense25);
         d_dense25 = nullptr;
-        dfree(d_z2);
-        d_z2 = nullptr;
     }
 
     static int chain(int n, int levels) { for (int l = 0; l < levels; ++l) n = (n + 1) / 2; return n; }
@@ -725,16 +716,7 @@ struct Solver : SolverBase {
             L.plane = (long long)L.rows * L.pitch;
             L.K = K;
             L.coef = L.x = L.b = nullptr;
-            L.label = nullptr; L.aggD = nullptr; L.aggS = nullptr;
-            L.x2 = nullptr;
             CU(dmalloc(&L.coef, (size_t)L.plane * 25 * sizeof(T)));
-            if (mg25_rowgs) {
-                T* alt = nullptr;
-                CU(dmalloc(&alt, (size_t)L.plane * K * sizeof(T)));
-                CU(cudaMemsetAsync(alt, 0, (size_t)L.plane * K * sizeof(T), stream));
-                if (level == 0) d_z2 = alt;
-                L.x2 = alt;
-            }
             if (level > 0) {
                 CU(dmalloc(&L.x, (size_t)L.plane * K * sizeof(T)));
                 CU(dmalloc(&L.b, (size_t)L.plane * K * sizeof(T)));
@@ -744,9 +726,6 @@ struct Solver : SolverBase {
             dim3 cg((L.pitch + 127) / 128, L.rows);
             if (level == 0) assemble25_kernel<T><<<cg, 128, 0, stream>>>(grid(), L);
             else galerkin25_kernel<T><<<cg, 128, 0, stream>>>(Acc25<T>{lev25.back()}, L);
-            // interior diagonal of the unconstrained operator on this level: 20/16, a quarter per level (P^T A P of a
-            // 4th-order operator with bilinear P) -- the scale a coupling must exceed to count as stiff
-            if (level < mg25_agg_levels && (long long)r * c > 256) HGTRY(build_aggregates(L, 1.25 * pow(0.25, level)));
             lev25.push_back(L);
             if ((long long)r * c <= 256) break;
             r = (r + 1) / 2; c = (c + 1) / 2;
@@ -760,65 +739,7 @@ struct Solver : SolverBase {
         CU(cudaGetLastError());
         return HG_OK;
     }
-    // clusters of stiffly coupled pixels of a level (mg25.cuh); leaves L.label == nullptr if there are none
-    int build_aggregates(Lev25<T>& L, double ref_diag) {
-        if (!d_changed) CU(dmalloc(&d_changed, sizeof(int)));
-        CU(dmalloc(&L.label, (size_t)L.plane * sizeof(int)));
-        CU(dmalloc(&L.aggD, (size_t)L.plane * sizeof(double)));
-        const T thr = (T)(mg25_agg_theta * ref_diag);
-        dim3 pg((L.pitch + 255) / 256, L.rows);
-        agg_label_init_kernel<T><<<pg, 256, 0, stream>>>(L, thr);
-        int rounds = 0, changed = 1;
-        while (changed && rounds < 4096) {
-            CU(cudaMemsetAsync(d_changed, 0, sizeof(int), stream));
-            for (int s = 0; s < 4; ++s) agg_label_step_kernel<T><<<pg, 256, 0, stream>>>(L, thr, d_changed);
-            CU(cudaMemcpyAsync(&changed, d_changed, sizeof(int), cudaMemcpyDeviceToHost, stream));
-            CU(cudaStreamSynchronize(stream));
-            rounds += 4;
-        }
-        // sizes -> dissolve singletons and clusters above 64 pixels; no cluster left: the level goes without
-        int* scratch = nullptr;
-        unsigned long long* d_kept = nullptr;
-        unsigned long long kept = 0;
-        CU(dmalloc(&scratch, (size_t)L.plane * sizeof(int)));
-        CU(dmalloc(&d_kept, sizeof(unsigned long long)));
-        CU(cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long), stream));
-        agg_count_kernel<T><<<pg, 256, 0, stream>>>(L);
-        agg_prune_kernel<T><<<pg, 256, 0, stream>>>(L, 64.0, scratch, d_kept);
-        agg_commit_kernel<T><<<pg, 256, 0, stream>>>(L, scratch);
-        CU(cudaMemcpyAsync(&kept, d_kept, sizeof kept, cudaMemcpyDeviceToHost, stream));
-        CU(cudaStreamSynchronize(stream));
-        dfree(scratch); dfree(d_kept);
-        if (kept == 0) {
-            dfree(L.label); dfree(L.aggD);
-            L.label = nullptr; L.aggD = nullptr;
-            return HG_OK;
-        }
-        agg_diag_kernel<T><<<pg, 256, 0, stream>>>(L);
-        CU(dmalloc(&L.aggS, (size_t)L.plane * K * sizeof(double)));
-        CU(cudaMemsetAsync(L.aggS, 0, (size_t)L.plane * K * sizeof(double), stream));
-        CU(cudaGetLastError());
-        return HG_OK;
-    }
-    void agg25(const Lev25<T>& L, const int* done) {
-        if (!L.label) return;
-        dim3 pg((L.cols + 255) / 256, L.rows);
-        agg_zero_kernel<T><<<pg, 256, 0, stream>>>(L, done);
-        agg_resid_kernel<T><<<pg, 256, 0, stream>>>(L, done);
-        agg_apply_kernel<T><<<pg, 256, 0, stream>>>(L, done);
-        launches += 3;
-    }
     void gs25(Lev25<T>& L, bool forward, const int* done) {
-        if (mg25_rowgs && L.x2) {
-            // one launch per row colour; the iterate moves from L.x to L.x2, then the two swap roles
-            dim3 rg((L.cols + RG_SEG - 1) / RG_SEG, (L.rows + 2) / 3);
-            for (int s = 0; s < mg25_sweeps; ++s) {
-                for (int c = 0; c < 3; ++c) gs25_rows_kernel<T><<<rg, RG_THREADS, 0, stream>>>(L, L.x, L.x2, forward ? c : 2 - c, forward ? 1 : 0, done);
-                std::swap(L.x, L.x2);
-            }
-            launches += 3 * mg25_sweeps;
-            return;
-        }
         dim3 gg(((L.cols + 2) / 3 + 127) / 128, (L.rows + 2) / 3);
         for (int s = 0; s < mg25_sweeps; ++s)
             for (int c = 0; c < 9; ++c) gs25_kernel<T><<<gg, 128, 0, stream>>>(L, forward ? c : 8 - c, done);
@@ -827,12 +748,10 @@ struct Solver : SolverBase {
     // z = M^-1 r: one symmetric V-cycle from the zero guess on the 25-point hierarchy (level 0 works in place on z, r)
     int vcycle25(T* z, T* r, const int* done) {
         lev25[0].x = z; lev25[0].b = r;
-        if (mg25_rowgs) lev25[0].x2 = d_z2;
         CU(cudaMemsetAsync(z, 0, (size_t)plane * K * sizeof(T), stream));
         const int n = (int)lev25.size();
         for (int l = 0; l + 1 < n; ++l) {
             gs25(lev25[l], true, done);
-            agg25(lev25[l], done);
             const Lev25<T>& Lc = lev25[l + 1];
             resid_restrict25_kernel<T><<<dim3((Lc.pitch + 127) / 128, Lc.rows), 128, 0, stream>>>(lev25[l], Lc, done);
         }
@@ -840,12 +759,9 @@ struct Solver : SolverBase {
         coarsest_dense25_kernel<T><<<K, 256, Lb.rows * Lb.cols * sizeof(double), stream>>>(Lb, d_dense25, done);
         for (int l = n - 2; l >= 0; --l) {
             prolong_add25_kernel<T><<<dim3((lev25[l].cols + 255) / 256, lev25[l].rows), 256, 0, stream>>>(lev25[l], lev25[l + 1], done);
-            agg25(lev25[l], done);
             gs25(lev25[l], false, done);
         }
         launches += 2 * (n - 1) + 2;
-        // the double-buffered smoother may leave the result in the other buffer (odd number of sweeps in total)
-        if (lev25[0].x != z) CU(cudaMemcpyAsync(z, lev25[0].x, (size_t)plane * K * sizeof(T), cudaMemcpyDeviceToDevice, stream));
         return HG_OK;
     }
 

@@ -29,11 +29,6 @@ struct Lev25 {
     T* coef;   // 25 planes, plane (di + 2) * 5 + (dj + 2); a pixel whose centre coefficient is 0 is inactive
     T* x;      // K planes
     T* b;      // K planes
-    T* x2;     // K planes: the other half of the double buffer of the row-coloured smoother (gs25_rows_kernel), else nullptr
-    // aggregate correction for stiff couplings (finest levels only; nullptr elsewhere)
-    int* label;      // cluster root (a pixel index) of every pixel that has a strong coupling, -1 otherwise
-    double* aggD;    // at root pixels: sum of the cluster's block of A (v^T A v for the cluster's indicator v)
-    double* aggS;    // K planes, at root pixels: sum of the residual over the cluster
 };
 
 template <typename T>
@@ -268,231 +263,6 @@ coarsest_dense25_kernel(Lev25<T> L, const double* __restrict__ M, const int* __r
         double s = 0.0;
         for (int q = 0; q < n; ++q) s += row[q] * sb25[q];
         L.x[k * L.plane + (long long)(e / L.cols) * L.pitch + e % L.cols] = (T)s;
-    }
-}
-
-// ---- aggregate correction for stiff couplings ----------------------------------------------------------------
-// w_lsq = 1e5 gradient constraints tie pairs / small clusters of pixels together with couplings 10^5 times
-// the stencil's.  A point smoother fixes the difference within such a cluster at once but moves the
-// cluster's common value by O(1/w) per sweep, and bilinear interpolation cannot represent a two-pixel bump,
-// so plain multigrid crawls (1 700 PCG iterations).  Remedy, as line relaxation is for anisotropy: after the
-// Gauss-Seidel sweep, one Jacobi step in the span of the clusters' indicator vectors,
-//     x += sum_C  v_C (v_C^T r) / (v_C^T A v_C),        r = b - A x,
-// (before it on the way up, so the cycle stays symmetric).  Clusters are the connected components of the
-// couplings |a_pq| > threshold, found at setup by label propagation; Galerkin coarsening carries the stiff
-// couplings to the next levels, so the three finest levels get the correction.  175 instead of 1 157
-// iterations in the numpy prototype (96^2, w = 1e5); no effect where no coupling is strong.
-template <typename T>
-__global__ void __launch_bounds__(256)
-agg_label_init_kernel(Lev25<T> L, T thr) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
-    if (j >= L.pitch) return;
-    const long long o = (long long)i * L.pitch + j;
-    int lab = -1;
-    if (j < L.cols && L.coef[12 * L.plane + o] != T(0)) {
-        for (int c = 0; c < 25; ++c)
-            if (c != 12 && fabs((double)L.coef[c * L.plane + o]) > (double)thr) lab = (int)o;
-    }
-    L.label[o] = lab;
-    L.aggD[o] = 0.0;
-}
-// one round of label propagation over the strong couplings (min root wins); sets *changed
-template <typename T>
-__global__ void __launch_bounds__(256)
-agg_label_step_kernel(Lev25<T> L, T thr, int* __restrict__ changed) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
-    if (j >= L.cols) return;
-    const long long o = (long long)i * L.pitch + j;
-    int lab = L.label[o];
-    if (lab < 0) return;
-    int best = lab;
-    for (int di = -2; di <= 2; ++di)
-        for (int dj = -2; dj <= 2; ++dj) {
-            const int c = (di + 2) * 5 + (dj + 2);
-            if (c == 12 || !(fabs((double)L.coef[c * L.plane + o]) > (double)thr)) continue;
-            const int lq = L.label[o + (long long)di * L.pitch + dj];
-            if (lq >= 0) {
-                const int root = L.label[lq];          // pointer jumping: the neighbour's root's root
-                best = min(best, root >= 0 ? min(lq, root) : lq);
-            }
-        }
-    if (best < lab) { L.label[o] = best; *changed = 1; }
-}
-// cluster sizes (into aggD at the roots, as counts), then: clusters larger than `maxc` are dissolved -- near
-// percolation they span the grid, their indicator is no longer a local mode, and thousands of atomic adds
-// onto one root would serialise
-template <typename T>
-__global__ void __launch_bounds__(256)
-agg_count_kernel(Lev25<T> L) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
-    if (j >= L.cols) return;
-    const long long o = (long long)i * L.pitch + j;
-    const int lab = L.label[o];
-    if (lab >= 0) atomicAdd(&L.aggD[lab], 1.0);
-}
-template <typename T>
-__global__ void __launch_bounds__(256)
-agg_prune_kernel(Lev25<T> L, double maxc, int* __restrict__ scratch, unsigned long long* __restrict__ kept) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
-    if (j >= L.cols) return;
-    const long long o = (long long)i * L.pitch + j;
-    const int lab = L.label[o];
-    int out = lab;
-    if (lab >= 0) {
-        const double n = L.aggD[lab];
-        if (n < 2.0 || n > maxc) out = -1;
-        else atomicAdd(kept, 1ull);
-    }
-    scratch[o] = out;        // labels are read by other threads until everybody has looked: write to a copy
-}
-template <typename T>
-__global__ void __launch_bounds__(256)
-agg_commit_kernel(Lev25<T> L, const int* __restrict__ scratch) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
-    if (j >= L.pitch) return;
-    const long long o = (long long)i * L.pitch + j;
-    L.label[o] = j < L.cols ? scratch[o] : -1;
-    L.aggD[o] = 0.0;
-}
-// aggD[root] = sum over the cluster's pixels p, q of a_pq
-template <typename T>
-__global__ void __launch_bounds__(256)
-agg_diag_kernel(Lev25<T> L) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
-    if (j >= L.cols) return;
-    const long long o = (long long)i * L.pitch + j;
-    const int lab = L.label[o];
-    if (lab < 0) return;
-    double s = 0.0;
-    for (int di = -2; di <= 2; ++di)
-        for (int dj = -2; dj <= 2; ++dj) {
-            const T a = L.coef[((di + 2) * 5 + (dj + 2)) * L.plane + o];
-            if (a != T(0) && L.label[o + (long long)di * L.pitch + dj] == lab) s += (double)a;
-        }
-    atomicAdd(&L.aggD[lab], s);
-}
-template <typename T>
-__global__ void __launch_bounds__(256)
-agg_zero_kernel(Lev25<T> L, const int* __restrict__ done) {
-    if (done && *done) return;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
-    if (j >= L.cols) return;
-    const long long o = (long long)i * L.pitch + j;
-    if (L.label[o] == (int)o)
-        for (int k = 0; k < L.K; ++k) L.aggS[k * L.plane + o] = 0.0;
-}
-template <typename T>
-__global__ void __launch_bounds__(256)
-agg_resid_kernel(Lev25<T> L, const int* __restrict__ done) {
-    if (done && *done) return;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
-    if (j >= L.cols) return;
-    const long long o = (long long)i * L.pitch + j;
-    const int lab = L.label[o];
-    if (lab < 0) return;
-    T cf[25];
-#pragma unroll
-    for (int c = 0; c < 25; ++c) cf[c] = L.coef[c * L.plane + o];
-    for (int k = 0; k < L.K; ++k) {
-        const T* xk = L.x + k * L.plane;
-        double res = (double)L.b[k * L.plane + o];
-#pragma unroll
-        for (int di = -2; di <= 2; ++di)
-#pragma unroll
-            for (int dj = -2; dj <= 2; ++dj) {
-                const int c = (di + 2) * 5 + (dj + 2);
-                if (cf[c] != T(0)) res -= (double)cf[c] * (double)xk[o + (long long)di * L.pitch + dj];
-            }
-        atomicAdd(&L.aggS[k * L.plane + lab], res);
-    }
-}
-template <typename T>
-__global__ void __launch_bounds__(256)
-agg_apply_kernel(Lev25<T> L, const int* __restrict__ done) {
-    if (done && *done) return;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
-    if (j >= L.cols) return;
-    const long long o = (long long)i * L.pitch + j;
-    const int lab = L.label[o];
-    if (lab < 0) return;
-    const double d = L.aggD[lab];
-    if (!(d > 0.0)) return;
-    for (int k = 0; k < L.K; ++k) L.x[k * L.plane + o] += (T)(L.aggS[k * L.plane + lab] / d);
-}
-
-// ---- row-coloured Gauss-Seidel: one launch per ROW colour, the three column colours inside the block -------------
-// (HGRID_MG25_ROWGS=1; written after round 1's GPU budget was spent: compiled, NOT YET RUN on a GPU, off by default.)
-// The nine launches of gs25_kernel each touch every third pixel of every third row, so every 32-byte sector of the
-// 25 coefficient planes is fetched three times per sweep.  Here a block owns a segment of one row i = ci (mod 3) and
-// sweeps its three column colours in sequence, keeping the row in shared memory: the coefficients of the segment
-// come from DRAM once and from L1 / L2 twice.  Same-row dependencies across segment borders are met by recomputing
-// RG_H = 4 halo pixels on either side (first colour on s0-4 .. s1+4, second on s0-2 .. s1+2, third on the segment).
-// To keep that recomputation race-free the iterate is double-buffered: a launch reads the rows it sweeps, and the
-// rows not yet swept in this sweep, from `xin`, the rows already swept from `xout`, and writes `xout` only.  After
-// the three launches `xout` holds the whole new iterate.  The ordering is exactly that of the nine-colour sweep.
-#define RG_SEG 384
-#define RG_THREADS 128
-#define RG_H 4
-template <typename T>
-__global__ void __launch_bounds__(RG_THREADS)
-gs25_rows_kernel(Lev25<T> L, const T* __restrict__ xin, T* __restrict__ xout, int ci, int forward, const int* __restrict__ done) {
-    if (done && *done) return;
-    __shared__ T xs[RG_SEG + 2 * RG_H + 4];            // columns s0 - RG_H - 2 .. s0 + RG_SEG + RG_H + 1 of the row
-    const int i = 3 * blockIdx.y + ci;
-    if (i >= L.rows) return;
-    const int s0 = blockIdx.x * RG_SEG, s1 = min(s0 + RG_SEG, L.cols);
-    const int lo = s0 - RG_H - 2, nx = RG_SEG + 2 * RG_H + 4;
-    const long long orow = (long long)i * L.pitch;
-    for (int k = 0; k < L.K; ++k) {
-        const T* xi = xin + k * L.plane;
-        T* xo = xout + k * L.plane;
-        const T* bk = L.b + k * L.plane;
-        __syncthreads();
-        for (int e = threadIdx.x; e < nx; e += RG_THREADS) {
-            const int j = lo + e;
-            xs[e] = (j >= 0 && j < L.cols) ? xi[orow + j] : T(0);
-        }
-        __syncthreads();
-        for (int step = 0; step < 3; ++step) {
-            const int c = forward ? step : 2 - step;
-            const int h = RG_H - 2 * step;              // this colour is needed (and valid) on s0 - h .. s1 + h - 1
-            const int first = s0 - h;
-            const int jstart = first + ((c - (first % 3 + 3) % 3) + 3) % 3;
-            for (int j = jstart + 3 * (int)threadIdx.x; j < s1 + h; j += 3 * RG_THREADS) {
-                if (j < 0 || j >= L.cols) continue;
-                const long long o = orow + j;
-                const T c12 = L.coef[12 * L.plane + o];
-                if (!(c12 > T(0))) continue;
-                T v = bk[o];
-#pragma unroll
-                for (int di = -2; di <= 2; ++di) {
-                    // rows i + di, di != 0, have the other two row colours: swept already in this sweep?
-                    const int cr = ((ci + di) % 3 + 3) % 3;
-                    const bool swept = forward ? cr < ci : cr > ci;
-                    const T* src = swept ? xo : xi;
-#pragma unroll
-                    for (int dj = -2; dj <= 2; ++dj) {
-                        const int cc = (di + 2) * 5 + (dj + 2);
-                        if (cc == 12) continue;
-                        const T a = L.coef[cc * L.plane + o];
-                        if (a == T(0)) continue;                     // also: neighbours outside the grid
-                        v -= a * (di == 0 ? xs[j + dj - lo] : src[o + (long long)di * L.pitch + dj]);
-                    }
-                }
-                xs[j - lo] = v / c12;
-            }
-            __syncthreads();
-        }
-        for (int j = s0 + (int)threadIdx.x; j < s1; j += RG_THREADS) xo[orow + j] = xs[j - lo];
     }
 }
 

@@ -216,12 +216,10 @@ def test_bilaplacian_mg_iterations_do_not_grow_with_the_grid():
     assert its[2] < 120, its
 
 
-def test_bilaplacian_stiff_gradient_constraints_aggregate_correction(monkeypatch):
-    """solve_grid_linear's default w_lsq = 1e5 couples pixel pairs 10^5 times more strongly than the stencil
-    does.  The (experimental, opt-in) aggregate correction of mg25.cuh -- one Jacobi step on the clusters'
-    indicator vectors after the Gauss-Seidel sweep -- cuts the MG-PCG iteration count at this size; with and
-    without it the answer must be the
-    direct solver's (cond ~ 1e11, so two float64 solvers already differ by ~cond * eps: parity <= 2e-5 of the range)."""
+def test_bilaplacian_stiff_gradient_constraints():
+    """solve_grid_linear's default w_lsq = 1e5 couples pixel pairs 10^5 times more strongly than the stencil does: the
+    MG-PCG iteration count is large, but the answer is the direct solver's.  cond ~ 1e11 here, so
+    two float64 solvers already differ by ~cond * eps: parity <= 2e-5 of the range."""
     n = 128
     rng = np.random.default_rng(0)
     p = go.GridProblem(n, n, 1, True)
@@ -236,16 +234,11 @@ def test_bilaplacian_stiff_gradient_constraints_aggregate_correction(monkeypatch
     p.d_down[:-1, :, 0] = z[1:] - z[:-1]; p.d_right[:, :-1, 0] = z[:, 1:] - z[:, :-1]
     p.w_g = 1e5
     ref = go.solve_problem(p)
-    its = {}
-    for agg in ("3", "0"):
-        monkeypatch.setenv("HGRID_MG25_AGG", agg)
-        s = bilap_solver(p, "fp64", "multigrid")
-        out = s.solve(p.hard_vals, None, p.d_down, p.d_right, rtol=1e-11, maxiter=50000, allow_unconverged=True)
-        its[agg] = s.last_stats["iterations"]
-        assert s.last_stats["relres"] < 1e-9
-        assert rel_err(out, ref) < 2e-5
-        s.close()
-    assert its["3"] * 2 < its["0"], its
+    s = bilap_solver(p, "fp64", "multigrid")
+    out = s.solve(p.hard_vals, None, p.d_down, p.d_right, rtol=1e-11, maxiter=50000)
+    assert s.last_stats["relres"] < 1e-9
+    assert rel_err(out, ref) < 2e-5
+    s.close()
 
 
 @pytest.mark.parametrize("K", [1, 4, 5, 7])
