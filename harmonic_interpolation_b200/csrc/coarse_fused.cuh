@@ -84,7 +84,7 @@ __global__ void ccode_kernel(Coarse<T> L) {
 }
 
 // any active pixel within the tile grown by `halo`
-__global__ void ctile_activity_kernel(const uint8_t* __restrict__ code, int rows, int cols, int pitch, int halo,
+static __global__ void ctile_activity_kernel(const uint8_t* __restrict__ code, int rows, int cols, int pitch, int halo,
                                       uint8_t* __restrict__ active) {
     __shared__ int any;
     if (threadIdx.x == 0) any = 0;

@@ -72,7 +72,7 @@ __global__ void cs_refq_kernel(Coarse<T> L) {
 }
 
 // activity of the chunks of a level: bit 0 any active pixel in the chunk, bit 1 any within the chunk grown by one pixel
-__global__ void cs_activity_kernel(const uint8_t* __restrict__ code, int rows, int cols, int pitch, int cr, int ns, uint8_t* __restrict__ act) {
+static __global__ void cs_activity_kernel(const uint8_t* __restrict__ code, int rows, int cols, int pitch, int cr, int ns, uint8_t* __restrict__ act) {
     __shared__ int a0, a1;
     if (threadIdx.x == 0) a0 = a1 = 0;
     __syncthreads();

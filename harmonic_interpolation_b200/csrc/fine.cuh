@@ -42,7 +42,7 @@ namespace hg {
 
 // ---- setup ------------------------------------------------------------------------------------------
 // activity of the aligned tiles: any free pixel within the tile grown by `halo`
-__global__ void tile_activity_kernel(const uint8_t* __restrict__ flags, int rows, int cols, int pitch, int halo,
+static __global__ void tile_activity_kernel(const uint8_t* __restrict__ flags, int rows, int cols, int pitch, int halo,
                                      uint8_t* __restrict__ active) {
     __shared__ int any;
     if (threadIdx.x == 0) any = 0;

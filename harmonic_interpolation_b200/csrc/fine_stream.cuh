@@ -42,7 +42,7 @@ namespace hg {
 // activity of the chunks: 0 = no free pixel within the chunk grown by `halo` (skipped), 1 = simple
 // (every pixel the warp reads is hard or a regular interior pixel -- code 0xAA, no soft weight: the
 // lean code path), 2 = general
-__global__ void sl_activity_kernel(const uint8_t* __restrict__ flags, const uint8_t* __restrict__ code, int rows, int cols, int pitch,
+static __global__ void sl_activity_kernel(const uint8_t* __restrict__ flags, const uint8_t* __restrict__ code, int rows, int cols, int pitch,
                                    int halo, int ns, uint8_t* __restrict__ active) {
     __shared__ int any, general;
     if (threadIdx.x == 0) any = general = 0;
@@ -78,7 +78,7 @@ __global__ void sl_activity_kernel(const uint8_t* __restrict__ flags, const uint
 // the lists -- and with them every launch -- are the same from run to run): list `which` = [down lean | down general |
 // up lean | up general] at lists + which * n; counts[which] = its length.  split (slab mode with overlap): the down
 // lists hold the interior chunks first, then those whose rows touch a ghost band; counts[4 + which] = number of interior ones.
-__global__ void __launch_bounds__(1024)
+static __global__ void __launch_bounds__(1024)
 sl_task_lists_kernel(const uint8_t* __restrict__ up, const uint8_t* __restrict__ down, int n, int ns, int rows, int ghost_top,
                      int ghost_bottom, int split, int* __restrict__ lists, int* __restrict__ counts) {
     const int which = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

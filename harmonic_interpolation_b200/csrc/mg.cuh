@@ -368,7 +368,7 @@ __global__ void dense_fill_kernel(Coarse<T> L, double* __restrict__ M) {
 // will do.  A pivot that has collapsed (<= 1e-10 of its original diagonal) marks a dependent
 // unknown: it is set to zero by clearing its row, which yields the generalised inverse on
 // the independent set.
-__global__ void __launch_bounds__(1024) gauss_jordan_kernel(double* __restrict__ M, int n) {
+static __global__ void __launch_bounds__(1024) gauss_jordan_kernel(double* __restrict__ M, int n) {
     extern __shared__ double fac[];   // n factors + n original diagonals
     double* d0 = fac + n;
     const int w = 2 * n;

@@ -54,7 +54,7 @@ __device__ __forceinline__ double ordered_sum(const double* part, int n, double*
 // one-block scalar stage then adds the PRESUM_BLOCKS chunk sums.  Fixed order, deterministic.
 #define PRESUM_BLOCKS 128
 #define PRESUM_MIN 4096
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 presum_kernel(const int* __restrict__ done, const double* __restrict__ part, int n, long long stride, double* __restrict__ out) {
     if (done && *done) return;
     __shared__ double red[32];
@@ -78,7 +78,7 @@ __device__ __forceinline__ double stage_value(CgState* st, const double* part, i
 }
 
 // after q = A p:  alpha = rz / pq
-__global__ void cg_alpha_kernel(CgState* st, const double* __restrict__ part_pq, int nblk, long long stride, int K, int phase) {
+static __global__ void cg_alpha_kernel(CgState* st, const double* __restrict__ part_pq, int nblk, long long stride, int K, int phase) {
     if (st->done) return;
     __shared__ double red[32];
     for (int k = 0; k < K; ++k) {
@@ -109,7 +109,7 @@ __global__ void cg_alpha_kernel(CgState* st, const double* __restrict__ part_pq,
 // anchor byte: 2 hard, 1 free and anchored, 0 free and not (yet) anchored.
 __device__ __forceinline__ bool edge_open_down(unsigned f, int pen) { return !(f & HG_FLAG_CUT_DOWN) || (pen && (f & HG_FLAG_PEN_DOWN)); }
 __device__ __forceinline__ bool edge_open_right(unsigned f, int pen) { return !(f & HG_FLAG_CUT_RIGHT) || (pen && (f & HG_FLAG_PEN_RIGHT)); }
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 anchor_init_kernel(const uint8_t* __restrict__ flags, int rows, int cols, int pitch, int pen, uint8_t* __restrict__ anc) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
     if (j >= pitch) return;
@@ -127,7 +127,7 @@ anchor_init_kernel(const uint8_t* __restrict__ flags, int rows, int cols, int pi
 }
 // one round: every 32 x 32 tile (+ a one-pixel halo as it stands) is iterated to its local fixed point in shared memory
 #define ANC_T 32
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 anchor_spread_kernel(const uint8_t* __restrict__ flags, int rows, int cols, int pitch, int pen, uint8_t* __restrict__ anc, int* __restrict__ changed) {
     __shared__ uint8_t A[ANC_T + 2][ANC_T + 2];
     __shared__ uint8_t F[ANC_T + 2][ANC_T + 2];
@@ -164,7 +164,7 @@ anchor_spread_kernel(const uint8_t* __restrict__ flags, int rows, int cols, int 
     }
     if (mine) *changed = 1;
 }
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 anchor_count_kernel(const uint8_t* __restrict__ anc, int rows, int cols, int pitch, unsigned long long* __restrict__ count) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
     const bool loose = j < cols && anc[(long long)i * pitch + j] == 0;
@@ -173,7 +173,7 @@ anchor_count_kernel(const uint8_t* __restrict__ anc, int rows, int cols, int pit
 }
 
 // caller's rows x cols flag bytes -> the pitch-padded plane: padding columns are hard, edge bits that point outside the grid are dropped
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 pad_flags_kernel(const uint8_t* __restrict__ raw, uint8_t* __restrict__ flags, int rows, int cols, int pitch) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
     if (j >= pitch) return;
@@ -189,7 +189,7 @@ pad_flags_kernel(const uint8_t* __restrict__ raw, uint8_t* __restrict__ flags, i
 // ---- generic (any preconditioner) CG kernels ----------------------------------------------------
 // convergence check right after the x / r update, so that the preconditioner launches that follow
 // turn into no-ops once the tolerance is met
-__global__ void cg_check_kernel(CgState* st, const double* __restrict__ part_rr, int nblk, long long stride, int K, int phase) {
+static __global__ void cg_check_kernel(CgState* st, const double* __restrict__ part_rr, int nblk, long long stride, int K, int phase) {
     if (st->done) return;
     __shared__ double red[32];
     __shared__ int all_conv;
@@ -218,7 +218,7 @@ __global__ void cg_check_kernel(CgState* st, const double* __restrict__ part_rr,
 // Outer check on the TRUE residual r = b - A x (computed in the master precision): fixes the
 // reference norm bb at the first call, decides final convergence, and arms the next inner CG
 // run, which only has to reduce the residual by `inner_red` (fp32 storage cannot do better).
-__global__ void cg_outer_kernel(CgState* st, const double* __restrict__ part_rr, int nblk, long long stride, int K, int first,
+static __global__ void cg_outer_kernel(CgState* st, const double* __restrict__ part_rr, int nblk, long long stride, int K, int first,
                                 double inner_red2, int phase) {
     __shared__ double red[32];
     __shared__ int all_conv;
@@ -251,7 +251,7 @@ __global__ void cg_outer_kernel(CgState* st, const double* __restrict__ part_rr,
 }
 
 // after z = M^-1 r:  rz_new -> beta
-__global__ void cg_beta_rz_kernel(CgState* st, const double* __restrict__ part_rz, int nblk, long long stride, int K, int init, int phase) {
+static __global__ void cg_beta_rz_kernel(CgState* st, const double* __restrict__ part_rz, int nblk, long long stride, int K, int init, int phase) {
     if (st->done) return;
     __shared__ double red[32];
     for (int k = 0; k < K; ++k) {

@@ -274,7 +274,7 @@ __global__ void diag_kernel(Grid<T> g, int bilap, T* __restrict__ dinv) {
 
 // counts[0] = pixels with no axis term (all-zero rows of L_refl), counts[1] = pixels
 // referenced by no row, counts[2] = hard pixels, counts[3] = any cut bit seen
-__global__ void domain_check_kernel(const uint8_t* __restrict__ fl, int rows, int cols, int pitch, int bilap,
+static __global__ void domain_check_kernel(const uint8_t* __restrict__ fl, int rows, int cols, int pitch, int bilap,
                                     unsigned long long* __restrict__ counts) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
