@@ -336,8 +336,9 @@ struct CsWarp {
             a = row[J0]; b = row[J1];
         }
         EA[SLOT][0] = a; EA[SLOT][1] = b;
-        EA[SLOT][2] = sl_dn1(a);
     }
+    // the next lane's first column, fetched a step after the load (a shuffle of a value just loaded waits for HBM)
+    template <int SLOT> __device__ __forceinline__ void share_e() { EA[SLOT][2] = sl_dn1(EA[SLOT][0]); }
     template <int SO, int SP, int SE, typename CF> __device__ __forceinline__ void up_odd(const CF& cf, const V4<T>& bO) {
         update<CF_ALL8, 1>(cf, C[SO], X[SO], bO, X[SP], L3[SP], R0[SP], L3[SO], R0[SO], X[SE], L3[SE], R0[SE]);
         L3u[SO] = sl_up1(X[SO].v[3]);
@@ -364,6 +365,7 @@ struct CsWarp {
             request(2 * j + 5, more ? C[A5] : 0u, more ? C[A6] : 0u);
         }
         const int m = (rbase >> 1) + j;
+        share_e<E1>();                             // loaded by the previous step
         load_e<EN>(m + 2);
         prefetch_coefs(2 * j + 3, C[(2 * U + 3) % 12]);
         prefetch_coefs(2 * j + 4, C[(2 * U + 4) % 12]);
@@ -407,6 +409,7 @@ struct CsWarp {
         request(3, C[3], C[4]);
         load_e<0>(rbase >> 1);
         load_e<1>((rbase >> 1) + 1);
+        share_e<0>();
 #pragma unroll 1
         for (int jb = 0; jb < nsteps; jb += 12) {
             step_up<0>(jb, nsteps); step_up<1>(jb + 1, nsteps); step_up<2>(jb + 2, nsteps); step_up<3>(jb + 3, nsteps);

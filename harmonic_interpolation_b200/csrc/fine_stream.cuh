@@ -125,6 +125,27 @@ sl_task_lists_kernel(const uint8_t* __restrict__ up, const uint8_t* __restrict__
     if (tid == 0) counts[which] = base;
 }
 
+// Lean mask words: word (g, qc) describes rows 8g .. 8g+7 of the quad of pixels 4qc .. 4qc+3: bit 4 (row & 7) + p is set where the
+// pixel is free (code byte != 0).  The lean kernels read ONE word per lane and eight rows instead of a code word per row: the
+// word of a row group is loaded a whole group ahead, so no request of the row FIFO waits for a load (the code-word loads were
+// the long-scoreboard stalls of round 1), and the masks cost 1/8 byte of HBM traffic per pixel instead of 1.
+static __global__ void sl_qmask_kernel(const uint8_t* __restrict__ code, int rows, int pitch, unsigned* __restrict__ qmask) {
+    const int qp = pitch >> 2, qc = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
+    if (qc >= qp) return;
+    unsigned w = 0u;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int i = 8 * g + r;
+        if (i < rows) {
+            const unsigned cw = *reinterpret_cast<const unsigned*>(code + ((long long)i * pitch + 4 * qc));
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if ((cw >> (8 * q)) & 0xffu) w |= 1u << (4 * r + q);
+        }
+    }
+    qmask[(long long)g * qp + qc] = w;
+}
+
 template <typename T> __device__ __forceinline__ T sl_up1(T v) { return __shfl_up_sync(HG_FULL, v, 1); }
 template <typename T> __device__ __forceinline__ T sl_dn1(T v) { return __shfl_down_sync(HG_FULL, v, 1); }
 
@@ -290,6 +311,11 @@ __device__ __forceinline__ void sl_cp16(void* smem, const void* gmem, bool valid
     const int bytes = valid ? 16 : 0;        // 0: nothing is read, the 16 bytes are zero-filled
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(bytes) : "memory");
 }
+// the same with the `ignore-src` predicate of cp.async (zeros are written, the source is not accessed): no size arithmetic
+__device__ __forceinline__ void sl_cp16p(void* smem, const void* gmem, unsigned valid) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("{ .reg .pred p; setp.eq.u32 p, %2, 0; cp.async.cg.shared.global [%0], [%1], 16, p; }" ::"r"(sa), "l"(gmem), "r"(valid) : "memory");
+}
 __device__ __forceinline__ void sl_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void sl_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -298,16 +324,39 @@ template <int N> __device__ __forceinline__ void sl_cp_wait() { asm volatile("cp
 
 template <typename T>
 struct SlLean {
-    const uint8_t* code;
+    const uint8_t* code;  // code bytes (the GENERAL stencil kernel only)
+    const unsigned* qm;   // lean mask words (sl_qmask_kernel)
     const T* rk;
     T* ring;              // this lane's quad in slot 0 of the warp's ring of r rows (shared memory); slots are 128 T apart
     int rows, pitch, c0, i0;
+    int qp, qg;           // mask words per row group, number of row groups
     bool colin, owner;
     V4<T> Z[8];
-    unsigned M[8];
+    unsigned M[8];        // code words of the rows in flight (the GENERAL stencil kernel only)
+    // Mask words of the row groups G0 - 1 .. G0 + 2 and (prefetched) G0 + 3, G0 = (first row of the current block of eight
+    // steps) >> 3.  A row is named by its offset O from row 8 G0 (-8 <= O < 24): its ring slot is O & 7, its word W[(O + 8) >> 3].
+    unsigned W[4], Wn;
     __device__ __forceinline__ unsigned load_code(int i) const {
         // (32-bit element offsets on the lean paths: the host only takes them when rows * pitch < 2^31)
         return (colin && (unsigned)i < (unsigned)rows) ? *reinterpret_cast<const unsigned*>(code + (i * pitch + c0)) : 0u;
+    }
+    __device__ __forceinline__ unsigned load_word(int g) const {
+        return (colin && (unsigned)g < (unsigned)qg) ? __ldg(qm + (g * qp + (c0 >> 2))) : 0u;
+    }
+    __device__ __forceinline__ void words_init(int ib) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) W[k] = load_word((ib >> 3) - 1 + k);
+    }
+    __device__ __forceinline__ void words_prefetch(int ib) { Wn = load_word((ib >> 3) + 3); }          // top of a block of eight steps
+    __device__ __forceinline__ void words_rotate() { W[0] = W[1]; W[1] = W[2]; W[2] = W[3]; W[3] = Wn; }   // end of the block
+    // non-zero if the quad of row O holds a free pixel / if its pixel P is free
+    template <int O> __device__ __forceinline__ unsigned quad() const {
+        static_assert(O >= -8 && O < 24, "row offset outside the mask words held");
+        return W[(O + 8) >> 3] & (0xFu << (4 * ((O + 8) & 7)));
+    }
+    template <int O, int P> __device__ __forceinline__ unsigned pix() const {
+        static_assert(O >= -8 && O < 24, "row offset outside the mask words held");
+        return W[(O + 8) >> 3] & (1u << (4 * ((O + 8) & 7) + P));
     }
     // request row i of r into slot `slot` (zeros where the quad has no free pixel); one commit group per row
     __device__ __forceinline__ void request(int i, int slot, unsigned m) {
@@ -320,29 +369,44 @@ struct SlLean {
         if (sizeof(T) == 8) sl_cp16(dst + 2, src + 2, m != 0u);
         sl_cp_commit();
     }
+    // The lean form: rows are requested in order, so the source is a running pointer (rq: this lane's quad of the next row to
+    // request), and the mask words are already zero outside the grid and the pitch -- no row test, no address arithmetic.
+    const T* rq;
+    __device__ __forceinline__ void request_start(int i) { rq = rk + ((long long)i * pitch + c0); }
+    __device__ __forceinline__ void request_next(int slot, unsigned m) {
+        T* dst = ring + slot * 128;
+        sl_cp16p(dst, rq, m);
+        if (sizeof(T) == 8) sl_cp16p(dst + 2, rq + 2, m);
+        sl_cp_commit();
+        rq += pitch;
+    }
     __device__ __forceinline__ V4<T> row(int slot) const { return ld4(ring + slot * 128); }
-    __device__ __forceinline__ void init(int ibeg, int slot0) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { Z[q] = zero4<T>(); M[q] = 0u; }
-        // codes of rows ibeg .. ibeg + SL_PD + 1, r of rows ibeg .. ibeg + SL_PD - 1  (slot0 = ibeg & 7, a compile-time fact of the caller)
-#pragma unroll
-        for (int q = 0; q < SL_PD + 2; ++q) M[(slot0 + q) & 7] = load_code(ibeg + q);
-#pragma unroll
-        for (int q = 0; q < SL_PD; ++q) request(ibeg + q, (slot0 + q) & 7, M[(slot0 + q) & 7]);
+    template <int S0, int Q> __device__ __forceinline__ void init_requests(int ibeg) {
+        if constexpr (Q < SL_PD) {
+            request_next((S0 + Q) & 7, quad<S0 + Q>());
+            init_requests<S0, Q + 1>(ibeg);
+        }
     }
-    // at the top of step i (slot C): code of row i + SL_PD + 2, request for row i + SL_PD; returns row i of r
-    template <int C> __device__ __forceinline__ V4<T> advance(int i) {
-        M[(C + SL_PD + 2) & 7] = load_code(i + SL_PD + 2);
-        request(i + SL_PD, (C + SL_PD) & 7, M[(C + SL_PD) & 7]);
+    // S0 = ibeg & 7 (a compile-time fact of the caller): mask words of the first block, r of rows ibeg .. ibeg + SL_PD - 1
+    template <int S0> __device__ __forceinline__ void init(int ibeg) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) Z[q] = zero4<T>();
+        words_init(ibeg);
+        request_start(ibeg);
+        init_requests<S0, 0>(ibeg);
+    }
+    // at the top of the step of row i (offset O): request for row i + SL_PD; returns row i of r
+    template <int O> __device__ __forceinline__ V4<T> advance(int i) {
+        request_next((O + SL_PD) & 7, quad<O + SL_PD>());
         sl_cp_wait<SL_PD>();
-        return row(C);
+        return row(O & 7);
     }
-    // red pixels of row i (slot C): z = r (+ add) where free
-    template <int C, int PAR> __device__ __forceinline__ void red_first(const V4<T>& rc, const T addA, const T addB) {
-        const unsigned m = M[C];
+    // red pixels of row O: z = r (+ add) where free
+    template <int O, int PAR> __device__ __forceinline__ void red_first(const V4<T>& rc, const T addA, const T addB) {
+        constexpr int C = (O + 8) & 7;
         Z[C] = zero4<T>();
-        Z[C].v[PAR] = (m & (0xffu << (8 * PAR))) ? rc.v[PAR] + addA : T(0);
-        Z[C].v[PAR + 2] = (m & (0xffu << (8 * (PAR + 2)))) ? rc.v[PAR + 2] + addB : T(0);
+        Z[C].v[PAR] = pix<O, PAR>() ? rc.v[PAR] + addA : T(0);
+        Z[C].v[PAR + 2] = pix<O, PAR + 2>() ? rc.v[PAR + 2] + addB : T(0);
     }
     // 1/4 of the four neighbours of the pixels PAR, PAR + 2 of slot C (rows above / below: slots CU, CD)
     template <int C, int CU, int CD, int PAR> __device__ __forceinline__ void nsum(T& nA, T& nB) const {
@@ -352,13 +416,13 @@ struct SlLean {
         nA = T(0.25) * ((Z[CU].v[PAR] + Z[CD].v[PAR]) + (lfA + rtA));
         nB = T(0.25) * ((Z[CU].v[PAR + 2] + Z[CD].v[PAR + 2]) + (lfB + rtB));
     }
-    // Gauss-Seidel update of the pixels PAR, PAR + 2 of slot C with right-hand side rc
-    template <int C, int CU, int CD, int PAR> __device__ __forceinline__ void update(const V4<T>& rc) {
+    // Gauss-Seidel update of the pixels PAR, PAR + 2 of row O with right-hand side rc
+    template <int O, int PAR> __device__ __forceinline__ void update(const V4<T>& rc) {
+        constexpr int C = (O + 8) & 7, CU = (O + 7) & 7, CD = (O + 9) & 7;
         T nA, nB;
         nsum<C, CU, CD, PAR>(nA, nB);
-        const unsigned m = M[C];
-        Z[C].v[PAR] = (m & (0xffu << (8 * PAR))) ? rc.v[PAR] + nA : T(0);
-        Z[C].v[PAR + 2] = (m & (0xffu << (8 * (PAR + 2)))) ? rc.v[PAR + 2] + nB : T(0);
+        Z[C].v[PAR] = pix<O, PAR>() ? rc.v[PAR] + nA : T(0);
+        Z[C].v[PAR + 2] = pix<O, PAR + 2>() ? rc.v[PAR + 2] + nB : T(0);
     }
 };
 
@@ -373,19 +437,19 @@ struct SlLeanDown : SlLean<T> {
     V4<T> S[8];
 
     template <int U> __device__ __forceinline__ void step(int ib) {     // ib = i0 - 3 (mod 8: 5)
-        constexpr int C = (5 + U) & 7, C1 = (C + 7) & 7, C2 = (C + 6) & 7, C3 = (C + 5) & 7, C4 = (C + 4) & 7;
+        constexpr int O = 5 + U;
+        constexpr int C = O & 7, C1 = (C + 7) & 7, C2 = (C + 6) & 7, C3 = (C + 5) & 7, C4 = (C + 4) & 7;
         constexpr int PAR = (5 + U) & 1;
         const int i = ib + U;
-        const V4<T> rc = B::template advance<C>(i);
-        B::template red_first<C, PAR>(rc, T(0), T(0));
-        B::template update<C1, C2, C, PAR>(B::row(C1));        // black pixels of row i - 1
+        const V4<T> rc = B::template advance<O>(i);
+        B::template red_first<O, PAR>(rc, T(0), T(0));
+        B::template update<O - 1, PAR>(B::row(C1));            // black pixels of row i - 1
         {   // residual at the red pixels of row i - 2
             T nA, nB;
             B::template nsum<C2, C3, C1, PAR>(nA, nB);
-            const unsigned m = B::M[C2];
             S[C2] = zero4<T>();
-            S[C2].v[PAR] = (m & (0xffu << (8 * PAR))) ? nA : T(0);
-            S[C2].v[PAR + 2] = (m & (0xffu << (8 * (PAR + 2)))) ? nB : T(0);
+            S[C2].v[PAR] = B::template pix<O - 2, PAR>() ? nA : T(0);
+            S[C2].v[PAR + 2] = B::template pix<O - 2, PAR + 2>() ? nB : T(0);
         }
         if (PAR == 1) {
             const int ic = i - 3, I = ic >> 1;
@@ -409,10 +473,12 @@ struct SlLeanDown : SlLean<T> {
     __device__ __forceinline__ void run() {
 #pragma unroll
         for (int q = 0; q < 8; ++q) S[q] = zero4<T>();
-        B::init(B::i0 - 3, 5);
+        B::template init<5>(B::i0 - 3);
 #pragma unroll 1
         for (int ib = B::i0 - 3; ib < B::i0 + SL_R + 3; ib += 8) {
+            B::words_prefetch(ib);
             step<0>(ib); step<1>(ib); step<2>(ib); step<3>(ib); step<4>(ib); step<5>(ib); step<6>(ib); step<7>(ib);
+            B::words_rotate();
         }
         sl_cp_wait<0>();
     }
@@ -427,6 +493,7 @@ struct SlLeanUp : SlLean<T> {
     double acc;
     T E[4][3];        // coarse rows, slot I & 3: the lane's two columns and the next lane's first
 
+    // (the next lane's first column is NOT fetched here: a shuffle of a value just loaded waits for HBM -- share_e, two steps later)
     template <int SLOT> __device__ __forceinline__ void load_e(int I) {
         T a = T(0), b = T(0);
         if (ek) {
@@ -436,40 +503,48 @@ struct SlLeanUp : SlLean<T> {
             a = row[J0]; b = row[J1];
         }
         E[SLOT][0] = a; E[SLOT][1] = b;
-        E[SLOT][2] = sl_dn1(a);
     }
+    template <int SLOT> __device__ __forceinline__ void share_e() { E[SLOT][2] = sl_dn1(E[SLOT][0]); }
     template <int U> __device__ __forceinline__ void step(int ib) {     // ib = i0 - 2 (mod 8: 6)
-        constexpr int C = (6 + U) & 7, C1 = (C + 7) & 7, C2 = (C + 6) & 7, C3 = (C + 5) & 7;
+        constexpr int O = 6 + U;
+        constexpr int C = O & 7, C1 = (C + 7) & 7, C2 = (C + 6) & 7;
         constexpr int PAR = U & 1;
         constexpr int EA = (3 + U / 2) & 3, EB = (EA + 1) & 3, EN = (EA + 2) & 3;      // (ib >> 1) & 3 == 3
         const int i = ib + U;
-        const V4<T> rc = B::template advance<C>(i);
+        const V4<T> rc = B::template advance<O>(i);
         if (PAR == 0) {
+            share_e<EB>();                      // loaded two steps ago, first needed by the next (odd) step
             load_e<EN>((i >> 1) + 2);
-            B::template red_first<C, 0>(rc, E[EA][0], E[EA][1]);
+            B::template red_first<O, 0>(rc, E[EA][0], E[EA][1]);
         } else {
-            B::template red_first<C, 1>(rc, T(0.25) * ((E[EA][0] + E[EA][1]) + (E[EB][0] + E[EB][1])),
+            B::template red_first<O, 1>(rc, T(0.25) * ((E[EA][0] + E[EA][1]) + (E[EB][0] + E[EB][1])),
                                         T(0.25) * ((E[EA][1] + E[EA][2]) + (E[EB][1] + E[EB][2])));
         }
-        B::template update<C1, C2, C, PAR>(B::row(C1));        // black pixels of row i - 1
+        B::template update<O - 1, PAR>(B::row(C1));            // black pixels of row i - 1
         const V4<T> r2 = B::row(C2);
-        B::template update<C2, C3, C1, PAR>(r2);               // red pixels of row i - 2 again
+        B::template update<O - 2, PAR>(r2);                    // red pixels of row i - 2 again
         const int io = i - 2;
-        if (io >= B::i0 && io < B::i0 + SL_R && B::owner && B::M[C2]) {
+        if (io >= B::i0 && io < B::i0 + SL_R && B::owner && B::template quad<O - 2>()) {
             // the row's four products in T, then fp64 (conversions and fp64 adds are the slow instructions here)
             const T part = (B::Z[C2].v[0] * r2.v[0] + B::Z[C2].v[1] * r2.v[1]) + (B::Z[C2].v[2] * r2.v[2] + B::Z[C2].v[3] * r2.v[3]);
             acc += (double)part;
-            st4(zk + (io * B::pitch + B::c0), B::Z[C2]);
+            st4(zo, B::Z[C2]);
         }
+        zo += B::pitch;
     }
+    T* zo;            // this lane's quad of z in the row that becomes final in the current step (running pointer)
     __device__ __forceinline__ void run() {
         acc = 0.0;
-        B::init(B::i0 - 2, 6);
+        zo = zk + ((long long)(B::i0 - 4) * B::pitch + B::c0);
+        B::template init<6>(B::i0 - 2);
         load_e<3>((B::i0 - 2) >> 1);
         load_e<0>(((B::i0 - 2) >> 1) + 1);
+        share_e<3>();
 #pragma unroll 1
         for (int ib = B::i0 - 2; ib < B::i0 + SL_R + 2; ib += 8) {
+            B::words_prefetch(ib);
             step<0>(ib); step<1>(ib); step<2>(ib); step<3>(ib); step<4>(ib); step<5>(ib); step<6>(ib); step<7>(ib);
+            B::words_rotate();
         }
         sl_cp_wait<0>();
     }
@@ -484,8 +559,8 @@ template <typename T> __device__ __forceinline__ T* sl_ring() {
 // One warp per task (chunk) and channel; `tasks` lists the chunks of one kind (lean or general).
 template <typename T, bool SOFT, bool LEAN>
 __global__ void __launch_bounds__(32 * SL_WPB, LEAN ? (sizeof(T) == 4 ? 4 : 2) : 1)
-sl_down_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict__ r, Coarse<T> cl, const int* __restrict__ tasks,
-               int ntasks, int ns, int zero_x, const int* __restrict__ done) {
+sl_down_kernel(Grid<T> g, const uint8_t* __restrict__ code, const unsigned* __restrict__ qmask, const T* __restrict__ r, Coarse<T> cl,
+               const int* __restrict__ tasks, int ntasks, int ns, int zero_x, const int* __restrict__ done) {
     if (done && *done) return;
     const int wid = blockIdx.x * SL_WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;     // warp <-> (task, channel)
     const int idx = wid / g.K, k = wid - idx * g.K;
@@ -503,7 +578,7 @@ sl_down_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict_
     if (LEAN) {
         SlLeanDown<T> f;
         f.ring = sl_ring<T>();
-        f.code = code; f.rk = r + k * g.plane;
+        f.code = code; f.qm = qmask; f.qp = g.pitch >> 2; f.qg = (g.rows + 7) >> 3; f.rk = r + k * g.plane;
         f.rows = g.rows; f.pitch = g.pitch; f.i0 = t * SL_R;
         f.c0 = c0; f.colin = colin; f.owner = owner;
         f.bk = cl.b + k * cl.plane; f.xk = cl.x + k * cl.plane; f.ccode = cl.code; f.zero_x = zero_x;
@@ -618,8 +693,8 @@ struct SlUp {
 
 template <typename T, bool SOFT, bool LEAN>
 __global__ void __launch_bounds__(32 * SL_WPB, LEAN ? (sizeof(T) == 4 ? 3 : 1) : 1)
-sl_up_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict__ r, T* __restrict__ z, Coarse<T> cl, int have_coarse,
-             const int* __restrict__ tasks, int ntasks, int ns, int nt, double* __restrict__ part_rz, const int* __restrict__ done) {
+sl_up_kernel(Grid<T> g, const uint8_t* __restrict__ code, const unsigned* __restrict__ qmask, const T* __restrict__ r, T* __restrict__ z, Coarse<T> cl,
+             int have_coarse, const int* __restrict__ tasks, int ntasks, int ns, int nt, double* __restrict__ part_rz, const int* __restrict__ done) {
     if (done && *done) return;
     const int wid = blockIdx.x * SL_WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;     // warp <-> (task, channel)
     const int idx = wid / g.K, k = wid - idx * g.K;
@@ -631,7 +706,7 @@ sl_up_kernel(Grid<T> g, const uint8_t* __restrict__ code, const T* __restrict__ 
     if (LEAN) {
         SlLeanUp<T> f;
         f.ring = sl_ring<T>();
-        f.code = code; f.rk = r + k * g.plane; f.zk = z + k * g.plane;
+        f.code = code; f.qm = qmask; f.qp = g.pitch >> 2; f.qg = (g.rows + 7) >> 3; f.rk = r + k * g.plane; f.zk = z + k * g.plane;
         f.rows = g.rows; f.pitch = g.pitch; f.i0 = t * SL_R;
         f.c0 = c0; f.colin = colin; f.owner = owner;
         f.ek = have_coarse ? cl.x + k * cl.plane : nullptr;
@@ -673,63 +748,109 @@ struct SlLap : SlLean<TX> {
     double acc;
     V4<TX> P[8];
 
-    // does the lane's quad of a row matter, given the code words of the row above, the row itself, the row below?
+    // GENERAL (code words): does the lane's quad of a row matter, given the code words of the row above, the row itself, the row below?
     __device__ __forceinline__ unsigned need(unsigned up, unsigned mid, unsigned dn) const {
         if (MODE == 0) return mid;
         return up | mid | dn | sl_up1(mid >> 24) | sl_dn1(mid & 0xffu);
     }
+    // lean (mask words): the same for the row at offset R
+    template <int R> __device__ __forceinline__ unsigned needq() const {
+        if (MODE == 0) return B::template quad<R>();
+        return B::template quad<R - 1>() | B::template quad<R>() | B::template quad<R + 1>() | sl_up1(B::template pix<R, 3>()) | sl_dn1(B::template pix<R, 0>());
+    }
+    // (MODE 1 takes its mask from the neighbouring rows and lanes too: the row and the lane themselves are checked here --
+    // rows -1 and `rows` lie outside the plane, for the first / last channel outside the allocation)
+    template <int R> __device__ __forceinline__ void request_lean(int i) {
+        unsigned m = needq<R>();
+        if (MODE == 1 && ((unsigned)i >= (unsigned)B::rows || !B::colin)) m = 0u;
+        B::request_next(R & 7, m);
+    }
     template <int U> __device__ __forceinline__ void step(int ib) {     // ib = i0 (mod 8: 0)
         constexpr int C = U & 7, CU = (C + 7) & 7, CD = (C + 1) & 7;
         const int i = ib + U;
-        // code of row i + PD + 3, request for row i + 1 + PD, row i + 1 arrives
-        B::M[(C + PD + 3) & 7] = B::load_code(i + PD + 3);
-        B::request(i + 1 + PD, (C + 1 + PD) & 7, need(B::M[(C + PD) & 7], B::M[(C + 1 + PD) & 7], B::M[(C + 2 + PD) & 7]));
+        // request for row i + 1 + PD, row i + 1 arrives
+        if constexpr (GENERAL) {
+            B::M[(C + PD + 3) & 7] = B::load_code(i + PD + 3);
+            B::request(i + 1 + PD, (C + 1 + PD) & 7, need(B::M[(C + PD) & 7], B::M[(C + 1 + PD) & 7], B::M[(C + 2 + PD) & 7]));
+        } else {
+            request_lean<U + 1 + PD>(i + 1 + PD);
+        }
         sl_cp_wait<PD>();
         P[CD] = B::row(CD);
-        const unsigned m = B::M[C];
+        unsigned m;
+        if constexpr (GENERAL) m = B::M[C]; else m = B::template quad<U>();
         const TX lf0 = sl_up1(P[C].v[3]), rt3 = sl_dn1(P[C].v[0]);
         if (i < B::i0 + SL_R && B::owner && m) {
             V4<TO> out;
             TX part = TX(0);
+            if constexpr (GENERAL) {
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                const unsigned cb = (m >> (8 * p)) & 0xffu;
-                const TX lf = p == 0 ? lf0 : P[C].v[p - 1], rt = p == 3 ? rt3 : P[C].v[p + 1];
-                TX v;
-                if (!GENERAL || cb == 0xAAu || cb == 0u) {
-                    v = cb ? P[C].v[p] - TX(0.25) * ((P[CU].v[p] + P[CD].v[p]) + (lf + rt)) : TX(0);
-                } else {
-                    TX wu, wd, wl, wr;
-                    decode(cb, wu, wd, wl, wr);
-                    v = (wu + wd + wl + wr) * P[C].v[p] - wu * P[CU].v[p] - wd * P[CD].v[p] - wl * lf - wr * rt;
+                for (int p = 0; p < 4; ++p) {
+                    const unsigned cb = (m >> (8 * p)) & 0xffu;
+                    const TX lf = p == 0 ? lf0 : P[C].v[p - 1], rt = p == 3 ? rt3 : P[C].v[p + 1];
+                    TX v;
+                    if (cb == 0xAAu || cb == 0u) {
+                        v = cb ? P[C].v[p] - TX(0.25) * ((P[CU].v[p] + P[CD].v[p]) + (lf + rt)) : TX(0);
+                    } else {
+                        TX wu, wd, wl, wr;
+                        decode(cb, wu, wd, wl, wr);
+                        v = (wu + wd + wl + wr) * P[C].v[p] - wu * P[CU].v[p] - wd * P[CD].v[p] - wl * lf - wr * rt;
+                    }
+                    if (MODE == 1) v = -v;
+                    out.v[p] = (TO)v;
+                    part += (MODE == 0 ? P[C].v[p] : v) * v;
                 }
-                if (MODE == 1) v = -v;
-                out.v[p] = (TO)v;
-                part += (MODE == 0 ? P[C].v[p] : v) * v;
+            } else {
+                const unsigned free4[4] = {B::template pix<U, 0>(), B::template pix<U, 1>(), B::template pix<U, 2>(), B::template pix<U, 3>()};
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const TX lf = p == 0 ? lf0 : P[C].v[p - 1], rt = p == 3 ? rt3 : P[C].v[p + 1];
+                    TX v = free4[p] ? P[C].v[p] - TX(0.25) * ((P[CU].v[p] + P[CD].v[p]) + (lf + rt)) : TX(0);
+                    if (MODE == 1) v = -v;
+                    out.v[p] = (TO)v;
+                    part += (MODE == 0 ? P[C].v[p] : v) * v;
+                }
             }
             acc += (double)part;
-            st4(qk + (i * B::pitch + B::c0), out);
+            st4(qo, out);
+        }
+        qo += B::pitch;
+    }
+    TO* qo;           // this lane's quad of the result in the current row (running pointer)
+    template <int Q> __device__ __forceinline__ void first_requests(int i0) {     // rows i0 - 1 .. i0 + PD
+        if constexpr (Q <= PD) {
+            request_lean<Q>(i0 + Q);
+            first_requests<Q + 1>(i0);
         }
     }
     __device__ __forceinline__ void run() {
         acc = 0.0;
         const int i0 = B::i0;
+        qo = qk + ((long long)i0 * B::pitch + B::c0);
 #pragma unroll
         for (int q = 0; q < 8; ++q) { P[q] = zero4<TX>(); B::M[q] = 0u; }
-        // codes of rows i0 - 2 .. i0 + PD + 2; the ring keeps rows i0 - 1 .. (slots 7, 0, 1, ...); operand rows i0 - 1 .. i0 + PD
-        unsigned cc[PD + 5];
+        if constexpr (GENERAL) {
+            // codes of rows i0 - 2 .. i0 + PD + 2; the ring keeps rows i0 - 1 .. (slots 7, 0, 1, ...); operand rows i0 - 1 .. i0 + PD
+            unsigned cc[PD + 5];
 #pragma unroll
-        for (int q = 0; q < PD + 5; ++q) cc[q] = B::load_code(i0 - 2 + q);
+            for (int q = 0; q < PD + 5; ++q) cc[q] = B::load_code(i0 - 2 + q);
 #pragma unroll
-        for (int q = -1; q < PD + 3; ++q) B::M[q & 7] = cc[q + 2];
+            for (int q = -1; q < PD + 3; ++q) B::M[q & 7] = cc[q + 2];
 #pragma unroll
-        for (int q = -1; q <= PD; ++q) B::request(i0 + q, q & 7, need(cc[q + 1], cc[q + 2], cc[q + 3]));
+            for (int q = -1; q <= PD; ++q) B::request(i0 + q, q & 7, need(cc[q + 1], cc[q + 2], cc[q + 3]));
+        } else {
+            B::words_init(i0);
+            B::request_start(i0 - 1);
+            first_requests<-1>(i0);
+        }
         sl_cp_wait<PD>();          // rows i0 - 1 and i0 have landed
         P[7] = B::row(7);
         P[0] = B::row(0);
 #pragma unroll 1
         for (int ib = i0; ib < i0 + SL_R; ib += 8) {
+            if constexpr (!GENERAL) B::words_prefetch(ib);
             step<0>(ib); step<1>(ib); step<2>(ib); step<3>(ib); step<4>(ib); step<5>(ib); step<6>(ib); step<7>(ib);
+            if constexpr (!GENERAL) B::words_rotate();
         }
         sl_cp_wait<0>();
     }
@@ -737,8 +858,8 @@ struct SlLap : SlLean<TX> {
 
 template <typename TX, typename TO, bool GENERAL, int MODE>
 __global__ void __launch_bounds__(32 * SL_WPB, sizeof(TX) == 4 ? 4 : 2)
-sl_lap_kernel(Grid<TO> g, const uint8_t* __restrict__ code, const TX* __restrict__ p, TO* __restrict__ q, const int* __restrict__ tasks,
-              int ntasks, int ns, int nt, double* __restrict__ part_pq, const int* __restrict__ done) {
+sl_lap_kernel(Grid<TO> g, const uint8_t* __restrict__ code, const unsigned* __restrict__ qmask, const TX* __restrict__ p, TO* __restrict__ q,
+              const int* __restrict__ tasks, int ntasks, int ns, int nt, double* __restrict__ part_pq, const int* __restrict__ done) {
     if (done && *done) return;
     const int wid = blockIdx.x * SL_WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int idx = wid / g.K, k = wid - idx * g.K;
@@ -746,7 +867,7 @@ sl_lap_kernel(Grid<TO> g, const uint8_t* __restrict__ code, const TX* __restrict
     const int task = tasks[idx], t = task / ns, s = task - t * ns;
     SlLap<TX, TO, GENERAL, MODE> f;
     f.ring = sl_ring<TX>();
-    f.code = code; f.rk = p + k * g.plane; f.qk = q + k * g.plane;
+    f.code = code; f.qm = qmask; f.qp = g.pitch >> 2; f.qg = (g.rows + 7) >> 3; f.rk = p + k * g.plane; f.qk = q + k * g.plane;
     f.rows = g.rows; f.pitch = g.pitch; f.i0 = t * SL_R;
     f.c0 = s * SL_OUT - 4 + 4 * lane;
     f.colin = f.c0 >= 0 && f.c0 < g.pitch;

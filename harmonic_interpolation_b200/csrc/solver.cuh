@@ -191,6 +191,7 @@ struct Solver : SolverBase {
     int tiles_x = 0, tiles_y = 0;
     uint8_t* d_down_active = nullptr;   // tiles with a free pixel within one pixel (restriction reaches that far)
     uint8_t* d_code = nullptr;          // one byte of edge-weight codes per pixel (fine.cuh)
+    unsigned* d_qmask = nullptr;        // lean mask words: free-pixel bits of 8 rows x 4 pixels (fine_stream.cuh: sl_qmask_kernel)
     double* d_lpart = nullptr;          // partial sums of the stencil kernel (two blocks per tile)
     // streaming legs (fine_stream.cuh): chunk activity (halo 0 / halo 1) and per-chunk partial sums of r.z
     uint8_t *d_sl_up = nullptr, *d_sl_down = nullptr;

@@ -169,8 +169,8 @@ int Solver<T>::build_tiles() {
     // inactive tiles never write their partial sums: they must read as zero
     CU(cudaMemsetAsync(d_tpart0, 0, (size_t)ntiles() * K * sizeof(double), stream));
     CU(cudaMemsetAsync(d_tpart1, 0, (size_t)ntiles() * K * sizeof(double), stream));
-    dfree(d_down_active); dfree(d_code); dfree(d_lpart);
-    d_down_active = d_code = nullptr; d_lpart = nullptr;
+    dfree(d_down_active); dfree(d_code); dfree(d_qmask); dfree(d_lpart);
+    d_down_active = d_code = nullptr; d_qmask = nullptr; d_lpart = nullptr;
     CU(dmalloc(&d_down_active, ntiles()));
     CU(dmalloc(&d_code, plane));
     CU(dmalloc(&d_lpart, (size_t)n_lap() * K * sizeof(double)));
@@ -178,6 +178,11 @@ int Solver<T>::build_tiles() {
     tile_activity_kernel<<<tile_grid(), 256, 0, stream>>>(d_flags, rows, cols, pitch, 0, d_tile_active);
     tile_activity_kernel<<<tile_grid(), 256, 0, stream>>>(d_flags, rows, cols, pitch, 1, d_down_active);
     opcode_kernel<T><<<dim3((pitch + 255) / 256, rows), 256, 0, stream>>>(grid(), d_code);
+    {
+        const int qp = pitch >> 2, qg = (rows + 7) >> 3;
+        CU(dmalloc(&d_qmask, (size_t)qp * qg * sizeof(unsigned)));
+        sl_qmask_kernel<<<dim3((qp + 127) / 128, qg), 128, 0, stream>>>(d_code, rows, pitch, d_qmask);
+    }
     sl_ns = (pitch + SL_OUT - 1) / SL_OUT;
     sl_nt = (rows + SL_R - 1) / SL_R;
     dfree(d_sl_up); dfree(d_sl_down); dfree(d_spart);
@@ -409,10 +414,10 @@ void Solver<T>::launch_sl_down(const Grid<T>& g, const T* r, const Coarse<T>& c1
     const int o_l = part == 2 ? sl_n_int[0] : 0, n_l = part == 1 ? sl_n_int[0] : sl_n_down_lean - o_l;
     const int o_g = part == 2 ? sl_n_int[1] : 0, n_g = part == 1 ? sl_n_int[1] : sl_n_down_gen - o_g;
     if (n_l > 0)
-        sl_down_kernel<T, false, true><<<sl_grid(n_l), sl_block(), sl_smem(), stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[0] + o_l, n_l, sl_ns, zx, done);
+        sl_down_kernel<T, false, true><<<sl_grid(n_l), sl_block(), sl_smem(), stream>>>(g, d_code, d_qmask, r, c1, d_sl_tasks + sl_off[0] + o_l, n_l, sl_ns, zx, done);
     if (n_g > 0) {
-        if (has_soft()) sl_down_kernel<T, true, false><<<sl_grid(n_g), sl_block(), 0, stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[1] + o_g, n_g, sl_ns, zx, done);
-        else sl_down_kernel<T, false, false><<<sl_grid(n_g), sl_block(), 0, stream>>>(g, d_code, r, c1, d_sl_tasks + sl_off[1] + o_g, n_g, sl_ns, zx, done);
+        if (has_soft()) sl_down_kernel<T, true, false><<<sl_grid(n_g), sl_block(), 0, stream>>>(g, d_code, d_qmask, r, c1, d_sl_tasks + sl_off[1] + o_g, n_g, sl_ns, zx, done);
+        else sl_down_kernel<T, false, false><<<sl_grid(n_g), sl_block(), 0, stream>>>(g, d_code, d_qmask, r, c1, d_sl_tasks + sl_off[1] + o_g, n_g, sl_ns, zx, done);
     }
     launches += (n_l > 0) + (n_g > 0) - (part == 2 ? 0 : 1);
 }
@@ -420,10 +425,10 @@ void Solver<T>::launch_sl_down(const Grid<T>& g, const T* r, const Coarse<T>& c1
 template <typename T>
 void Solver<T>::launch_sl_up(const Grid<T>& g, const T* r, T* z, const Coarse<T>& c1, int have_coarse, const int* done) {
     if (sl_n_up_lean)
-        sl_up_kernel<T, false, true><<<sl_grid(sl_n_up_lean), sl_block(), sl_smem(), stream>>>(g, d_code, r, z, c1, have_coarse, d_sl_tasks + sl_off[2], sl_n_up_lean, sl_ns, sl_nt, d_spart, done);
+        sl_up_kernel<T, false, true><<<sl_grid(sl_n_up_lean), sl_block(), sl_smem(), stream>>>(g, d_code, d_qmask, r, z, c1, have_coarse, d_sl_tasks + sl_off[2], sl_n_up_lean, sl_ns, sl_nt, d_spart, done);
     if (sl_n_up_gen) {
-        if (has_soft()) sl_up_kernel<T, true, false><<<sl_grid(sl_n_up_gen), sl_block(), 0, stream>>>(g, d_code, r, z, c1, have_coarse, d_sl_tasks + sl_off[3], sl_n_up_gen, sl_ns, sl_nt, d_spart, done);
-        else sl_up_kernel<T, false, false><<<sl_grid(sl_n_up_gen), sl_block(), 0, stream>>>(g, d_code, r, z, c1, have_coarse, d_sl_tasks + sl_off[3], sl_n_up_gen, sl_ns, sl_nt, d_spart, done);
+        if (has_soft()) sl_up_kernel<T, true, false><<<sl_grid(sl_n_up_gen), sl_block(), 0, stream>>>(g, d_code, d_qmask, r, z, c1, have_coarse, d_sl_tasks + sl_off[3], sl_n_up_gen, sl_ns, sl_nt, d_spart, done);
+        else sl_up_kernel<T, false, false><<<sl_grid(sl_n_up_gen), sl_block(), 0, stream>>>(g, d_code, d_qmask, r, z, c1, have_coarse, d_sl_tasks + sl_off[3], sl_n_up_gen, sl_ns, sl_nt, d_spart, done);
     }
     launches += (sl_n_up_lean > 0) + (sl_n_up_gen > 0) - 1;
 }
@@ -432,9 +437,9 @@ template <typename T>
 void Solver<T>::launch_sl_lap(const T* p, T* q, const int* done) {
     const Grid<T> g = grid();
     if (sl_n_up_lean)
-        sl_lap_kernel<T, T, false, 0><<<sl_grid(sl_n_up_lean), sl_block(), sl_smem(), stream>>>(g, d_code, p, q, d_sl_tasks + sl_off[2], sl_n_up_lean, sl_ns, sl_nt, d_spart2, done);
+        sl_lap_kernel<T, T, false, 0><<<sl_grid(sl_n_up_lean), sl_block(), sl_smem(), stream>>>(g, d_code, d_qmask, p, q, d_sl_tasks + sl_off[2], sl_n_up_lean, sl_ns, sl_nt, d_spart2, done);
     if (sl_n_up_gen)
-        sl_lap_kernel<T, T, true, 0><<<sl_grid(sl_n_up_gen), sl_block(), sl_smem(), stream>>>(g, d_code, p, q, d_sl_tasks + sl_off[3], sl_n_up_gen, sl_ns, sl_nt, d_spart2, done);
+        sl_lap_kernel<T, T, true, 0><<<sl_grid(sl_n_up_gen), sl_block(), sl_smem(), stream>>>(g, d_code, d_qmask, p, q, d_sl_tasks + sl_off[3], sl_n_up_gen, sl_ns, sl_nt, d_spart2, done);
     launches += (sl_n_up_lean > 0) + (sl_n_up_gen > 0);
 }
 
@@ -444,9 +449,9 @@ void Solver<T>::launch_sl_resid(const double* x, T* r) {
     const Grid<T> g = grid();
     const size_t sm = (size_t)SL_WPB * SL_RING * 128 * sizeof(double);
     if (sl_n_up_lean)
-        sl_lap_kernel<double, T, false, 1><<<sl_grid(sl_n_up_lean), sl_block(), sm, stream>>>(g, d_code, x, r, d_sl_tasks + sl_off[2], sl_n_up_lean, sl_ns, sl_nt, d_spart2, nullptr);
+        sl_lap_kernel<double, T, false, 1><<<sl_grid(sl_n_up_lean), sl_block(), sm, stream>>>(g, d_code, d_qmask, x, r, d_sl_tasks + sl_off[2], sl_n_up_lean, sl_ns, sl_nt, d_spart2, nullptr);
     if (sl_n_up_gen)
-        sl_lap_kernel<double, T, true, 1><<<sl_grid(sl_n_up_gen), sl_block(), sm, stream>>>(g, d_code, x, r, d_sl_tasks + sl_off[3], sl_n_up_gen, sl_ns, sl_nt, d_spart2, nullptr);
+        sl_lap_kernel<double, T, true, 1><<<sl_grid(sl_n_up_gen), sl_block(), sm, stream>>>(g, d_code, d_qmask, x, r, d_sl_tasks + sl_off[3], sl_n_up_gen, sl_ns, sl_nt, d_spart2, nullptr);
     launches += (sl_n_up_lean > 0) + (sl_n_up_gen > 0);
 }
 

@@ -55,7 +55,7 @@ Solver<T>::~Solver() {
     dfree(d_z);
     if (kRefine) { dfree(d_xm); dfree(d_bm); }
     dfree(d_tile_active); dfree(d_tpart0); dfree(d_tpart1);
-    dfree(d_down_active); dfree(d_code); dfree(d_lpart);
+    dfree(d_down_active); dfree(d_code); dfree(d_qmask); dfree(d_lpart);
     dfree(d_sl_up); dfree(d_sl_down); dfree(d_spart); dfree(d_spart2); dfree(d_sl_tasks); dfree(d_task_counts);
     
     dfree(d_gl_rows); dfree(d_gsend);
