@@ -31,6 +31,11 @@ class Values(ctypes.Structure):
     _fields_ = [("hard_vals", _dp), ("soft_vals", _dp), ("d_down", _dp), ("d_right", _dp), ("x0", _dp), ("rhs", _dp)]
 
 
+class LinearConstraints(ctypes.Structure):
+    _fields_ = [("squared", ctypes.c_int), ("n_constraints", ctypes.c_int), ("row_ptr", ctypes.POINTER(ctypes.c_int)),
+                ("pixel", ctypes.POINTER(ctypes.c_int)), ("coeff", _dp), ("rhs", _dp), ("weight", ctypes.c_double)]
+
+
 class Stats(ctypes.Structure):
     _fields_ = [("iterations", ctypes.c_int), ("status", ctypes.c_int), ("relres", ctypes.c_double),
                 ("relres_cg", ctypes.c_double), ("solve_ms", ctypes.c_double), ("upload_ms", ctypes.c_double),
@@ -57,6 +62,8 @@ SYMBOLS = {
     "hg_setup": (ctypes.c_int, [_H, ctypes.POINTER(SetupInfo)]),
     "hg_apply": (ctypes.c_int, [_H, _dp, _dp]),
     "hg_solve": (ctypes.c_int, [_H, ctypes.POINTER(Values), _dp, ctypes.c_double, ctypes.c_int, ctypes.POINTER(Stats)]),
+    "hg_solve_composed": (ctypes.c_int, [_H, ctypes.POINTER(Values), ctypes.POINTER(LinearConstraints), _dp, ctypes.c_double, ctypes.c_int,
+                                         ctypes.POINTER(Stats)]),
     "hg_solve_u8": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_uint8), ctypes.c_double, ctypes.c_int, ctypes.POINTER(Stats)]),
     "hg_upload_values": (ctypes.c_int, [_H, ctypes.POINTER(Values), ctypes.POINTER(Stats)]),
     "hg_solve_device": (ctypes.c_int, [_H, ctypes.c_double, ctypes.c_int, ctypes.POINTER(Stats)]),

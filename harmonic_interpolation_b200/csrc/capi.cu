@@ -158,6 +158,20 @@ int hg_solve_u8(hg_handle h, const uint8_t* hard_vals, uint8_t* out, double rtol
     return rc;
 }
 
+int hg_solve_composed(hg_handle h, const hg_values* vals, const hg_linear_constraints* lc, double* x_out, double rtol,
+                      int maxiter, hg_stats* stats) {
+    CHECK_H(h);
+    hg_stats local;
+    memset(&local, 0, sizeof local);
+    hg_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof *st);
+    HGTRY(h->impl->upload(vals, st));
+    int rc = h->impl->solve_composed(lc, rtol, maxiter, st);
+    if (rc != HG_OK && rc != HG_ERR_NOT_CONVERGED) return rc;
+    HGTRY(h->impl->download(x_out, st));
+    return rc;
+}
+
 int hg_solve(hg_handle h, const hg_values* vals, double* x_out, double rtol, int maxiter, hg_stats* stats) {
     CHECK_H(h);
     hg_stats local;

@@ -1,5 +1,5 @@
 // solver.cuh -- the solver handle behind the C ABI of libhgrid.so (include/hgrid.h): state, small inline helpers and the
-// launch templates.  The member functions live in five translation units, compiled in parallel:
+// launch templates.  The member functions live in six translation units, compiled in parallel:
 //   solver_setup.cu   handle life cycle, pattern upload, hg_setup (domain checks, unconstrained components), value upload /
 //                     download, operator application, introspection
 //   solver_mg.cu      Laplacian path: code bytes / activity / task lists, the Galerkin hierarchy, the V-cycle and the
@@ -7,6 +7,7 @@
 //   solver_mg25.cu    bilaplacian path: the 25-point hierarchy and its V-cycle
 //   solver_slab.cu    multi-GPU slab mode: communicator, gather of the replicated levels, failure handling
 //   solver_pcg.cu     the scalar stages and the MG-PCG / refinement driver
+//   solver_composed.cu  the composed systems of poisson.py (squared Laplacian, constraint rows over several pixels)
 // capi.cu holds the extern "C" entry points, the error string and the run-time binding of NCCL.
 #pragma once
 #include <dlfcn.h>
@@ -116,6 +117,7 @@ struct SolverBase {
     virtual int apply(const double* x, double* y) = 0;
     virtual int upload(const hg_values* v, hg_stats* st) = 0;
     virtual int solve_device(double rtol, int maxiter, hg_stats* st) = 0;
+    virtual int solve_composed(const hg_linear_constraints* lc, double rtol, int maxiter, hg_stats* st) = 0;
     virtual int download(double* x, hg_stats* st) = 0;
     virtual int bench_apply(int iters, double* ms) = 0;
     virtual int mg_levels() = 0;
@@ -540,6 +542,8 @@ struct Solver : SolverBase {
     int sync_watchful();
     int solve_device(double rtol, int maxiter, hg_stats* st) override;
     int solve_device_impl(double rtol, int maxiter, hg_stats* st);
+    // (L^m + w A^T A) x = L^(m-1) g + w A^T c of poisson.py (solver_composed.cu)
+    int solve_composed(const hg_linear_constraints* lc, double rtol, int maxiter, hg_stats* st) override;
     int upload_u8(const uint8_t* vals, hg_stats* st) override;
     int download_u8(uint8_t* out, hg_stats* st) override;
     int reset_guess() override;

@@ -160,6 +160,52 @@ class GridSolver:
             C.check(code)
         return out
 
+    def solve_composed(self, constraints, weight, squared=False, hard_vals=None, rhs=None, x0=None, rtol=None, maxiter=None,
+                       accept=None):
+        """(L^m + weight A^T A) x = L^(m-1) rhs + weight A^T c (hg_solve_composed; poisson.py:55-89), m = 2 if `squared`.
+        L is this solver's Laplacian without its soft weights (they only shape the preconditioner).  constraints: a
+        sequence of (pixels, coeffs, c) rows -- row-major pixel indices, their coefficients, the (K,) right-hand side.
+        fp64 solvers only.  Raises ArithmeticError like `solve`; a solve that stagnates short of `rtol` is returned if its
+        true relative residual is at most `accept`."""
+        assert self.precision == "fp64"
+        ptr = np.zeros(len(constraints) + 1, np.int32)
+        pix, coef = [], []
+        c = np.zeros((max(len(constraints), 1), self.K), np.float64)
+        for n, (pixels, coeffs, value) in enumerate(constraints):
+            pixels = np.asarray(pixels, np.int64).ravel()
+            coeffs = np.asarray(coeffs, np.float64).ravel()
+            assert pixels.shape == coeffs.shape
+            pix.append(pixels); coef.append(coeffs)
+            ptr[n + 1] = ptr[n] + len(pixels)
+            c[n] = np.asarray(value, np.float64).reshape(self.K)
+        pix = np.ascontiguousarray(np.concatenate(pix) if pix else np.zeros(0), dtype=np.int32)
+        coef = np.ascontiguousarray(np.concatenate(coef) if coef else np.zeros(0), dtype=np.float64)
+        ip = ctypes.POINTER(ctypes.c_int)
+        lc = C.LinearConstraints(int(bool(squared)), len(constraints), ptr.ctypes.data_as(ip), pix.ctypes.data_as(ip), C.dptr(coef),
+                                 C.dptr(c), float(weight))
+        keep = [self._vals(a) for a in (hard_vals, None, None, None, x0, rhs)]
+        vals = C.Values(*[C.dptr(a) for a in keep])
+        out = np.empty((self.rows, self.cols, self.K), np.float64)
+        stats = C.Stats()
+        if rtol is None:
+            rtol = default_rtol(self.precision)
+        if maxiter is None:
+            maxiter = int(os.environ.get("HGRID_MAXITER", 0)) or max(5000, 40 * (self.rows + self.cols))
+        code = self._lib.hg_solve_composed(self._h, ctypes.byref(vals), ctypes.byref(lc), C.dptr(out), float(rtol), int(maxiter),
+                                           ctypes.byref(stats))
+        self.last_stats = stats.as_dict()
+        if code == C.ERR_BREAKDOWN:
+            raise ArithmeticError(C.last_error())
+        if code == C.ERR_NOT_CONVERGED:
+            if accept is None:
+                accept = accept_relres(self.precision)
+            if not (os.environ.get("HGRID_ALLOW_UNCONVERGED") or stats.relres <= accept):
+                raise ArithmeticError("%s (relative residual %.3e after %d iterations)" % (
+                    C.last_error(), stats.relres, stats.iterations))
+        else:
+            C.check(code)
+        return out
+
     def solve_u8(self, hard_vals_u8, out=None, rtol=None, maxiter=None):
         """Image form (hg_solve_u8): uint8 (rows, cols, K) in -- meaning u8 / 255 at hard pixels -- and
         uint8 out = clip(round(255 x)).  `out` may be a preallocated (e.g. pinned) uint8 array."""

@@ -139,6 +139,29 @@ int hg_apply(hg_handle h, const double* x, double* y);
  * (recovery.py:926-943, 993, 1059-1075, 1319-1327).  x_out is (rows, cols, K) float64. */
 int hg_solve(hg_handle h, const hg_values* vals, double* x_out, double rtol, int maxiter, hg_stats* stats);
 
+/* Composed systems of the reference's gradient-domain integrator, poisson.solve_poisson_simple (poisson.py:6-99):
+ *
+ *     ( L^m + weight A^T A ) x = L^(m-1) g + weight A^T c        m = 1, or 2 for `squared` (bilaplacian=True, poisson.py:65-67)
+ *
+ * L is the handle's Laplacian WITHOUT its soft weights (with HG_EDGES_UNIFORM: G.T*G / 4 of poisson.py:55-56, 204-251);
+ * g = vals->rhs (G.T * target_gradients of poisson.py:73, scaled like L); A holds the rows of generate_constraint_matrix
+ * (poisson.py:329-366) in CSR form, any number of pixels per row, c their right-hand sides, (n_constraints, K).  The
+ * handle's soft weights D only shape the preconditioner M = (L + D)^m: set D = diag(weight A^T A) for m = 1 and its
+ * square root for m = 2.  fp64, Laplacian + multigrid handles on one GPU; constraint rows must not touch hard pixels, and
+ * for m = 2 hard pixels must be separated from the free ones by cut edges (what a mask border of poisson.py is), so that
+ * eliminating them from L^2 equals squaring the reduced L.  vals->hard_vals and vals->x0 as in hg_solve. */
+typedef struct {
+    int squared;             /* 0: m = 1, 1: m = 2                                            */
+    int n_constraints;       /* rows of A                                                     */
+    const int* row_ptr;      /* n_constraints + 1 offsets into pixel / coeff (row_ptr[0] = 0) */
+    const int* pixel;        /* row-major pixel index i * cols + j of every entry             */
+    const double* coeff;     /* coefficient of every entry                                    */
+    const double* rhs;       /* (n_constraints, K) right-hand sides c                         */
+    double weight;           /* linear_constraints_weight (poisson.py:88-89), scaled like L^m */
+} hg_linear_constraints;
+int hg_solve_composed(hg_handle h, const hg_values* vals, const hg_linear_constraints* lc, double* x_out, double rtol,
+                      int maxiter, hg_stats* stats);
+
 /* Image form of hg_solve for hard-constraint fills (the CLI's pipeline, fill_alpha_harmonic.py:27-45,
  * 72-76): hard values arrive as uint8 (rows, cols, K) and mean u8 / 255; the result is returned as
  * uint8 = clip(round_half_even(255 x), 0, 255).  Soft / gradient value arrays are taken as zero.

@@ -576,14 +576,18 @@ def gradient_operator(rows, cols, mask=None):
     return sp.coo_matrix((np.concatenate(V), (np.concatenate(I), np.concatenate(J))), shape=(2 * rows * cols, rows * cols)).tocsr()
 
 
-def solve_poisson_simple(target_gradients, linear_constraints, linear_constraints_weight, mask=None, mask_value=None):
-    """poisson.py:6-99 (Laplacian form): system = G.T G (+ Dirichlet rows for masked pixels, poisson.py:76-82)
-    + w A.T A, rhs = G.T u + w A.T b (poisson.py:85-89, 329-366); sparse direct solve."""
+def solve_poisson_simple(target_gradients, linear_constraints, linear_constraints_weight, mask=None, mask_value=None, bilaplacian=False):
+    """poisson.py:6-99: system = G.T G -- or (G.T G)^2 with G <- G (G.T G) for `bilaplacian`, poisson.py:65-67 --
+    (+ Dirichlet rows for masked pixels, poisson.py:76-82) + w A.T A, rhs = G.T u + w A.T b (poisson.py:85-89, 329-366);
+    sparse direct solve."""
     u = np.asarray(target_gradients, float)
     rows, cols, _, K = u.shape
     N = rows * cols
     G = gradient_operator(rows, cols, mask)
     system = (G.T @ G).tocsr()
+    if bilaplacian:
+        G = (G @ system).tocsr()
+        system = (system.T @ system).tocsr()
     rhs = G.T @ u.reshape(N * 2, K)
     if mask is not None and mask_value is not None:
         c = np.flatnonzero(~np.asarray(mask, bool).ravel())

@@ -134,3 +134,109 @@ def test_tictoc_dec_and_nesting(capsys):
     assert lines[0] == "+ work" and lines[1] == "++ inner"
     assert lines[2].startswith("-- inner ") and lines[3].startswith("- work ")
     assert T.starts == []
+
+
+class _ScipyComposedSolver:
+    """TEST INFRASTRUCTURE: what libhgrid's hg_solve_composed is specified to compute (include/hgrid.h), assembled with scipy,
+    standing in for GridSolver so that the HOST side of poisson.solve_poisson_simple's composed path -- scaling, the
+    preconditioner diagonal, masked-out pixels that a constraint touches -- can be held to the reference's goldens on CPU."""
+    def __init__(self, rows, cols, channels=1, bilaplacian=False, precision=None, preconditioner=None, uniform_edges=False):
+        assert uniform_edges and not bilaplacian and precision == "fp64"
+        self.rows, self.cols, self.K = rows, cols, channels
+
+    def set_pattern(self, flags, soft_weights=None, soft_scalar=0.0, w_g=0.0):
+        self.flags, self.D = np.asarray(flags), soft_weights
+        assert ((self.D > 0) == ((self.flags & 32) != 0)).all()
+
+    def solve_composed(self, constraints, weight, squared=False, hard_vals=None, rhs=None, x0=None, rtol=None, maxiter=None, accept=None):
+        import scipy.sparse as sp
+        import scipy.sparse.linalg as spla
+        rows, cols, K, f = self.rows, self.cols, self.K, self.flags
+        N = rows * cols
+        idx = np.arange(N).reshape(rows, cols)
+        I, J = [], []
+        dn = (f[:-1] & 2) == 0
+        rt = (f[:, :-1] & 4) == 0
+        I += [idx[:-1][dn]]; J += [idx[1:][dn]]
+        I += [idx[:, :-1][rt]]; J += [idx[:, 1:][rt]]
+        I, J = np.concatenate(I), np.concatenate(J)
+        Wm = sp.coo_matrix((np.full(len(I), 0.25), (I, J)), shape=(N, N))
+        Wm = (Wm + Wm.T).tocsr()
+        L = (sp.diags(np.asarray(Wm.sum(1)).ravel()) - Wm).tocsr()
+        hard = (f & 1).astype(bool).ravel()
+        free = np.flatnonzero(~hard)
+        assert abs(L[free][:, np.flatnonzero(hard)]).sum() == 0        # hard pixels are cut off (needed for m = 2)
+        g = np.asarray(rhs, float).reshape(N, K)
+        A = sp.lil_matrix((len(constraints), N)); c = np.zeros((len(constraints), K))
+        for n, (pix, coef, val) in enumerate(constraints):
+            for p, cf in zip(pix, coef):
+                assert not hard[p]
+                A[n, p] += cf
+            c[n] = val
+        A = A.tocsr()
+        Lf = L[free][:, free]
+        S = (Lf @ Lf if squared else Lf) + weight * (A.T @ A)[free][:, free]
+        b = (Lf @ g[free] if squared else g[free]) + weight * (A.T @ c)[free]
+        x = np.zeros((N, K))
+        if hard_vals is not None:
+            x[hard] = np.asarray(hard_vals, float).reshape(N, K)[hard]
+        x[free] = spla.splu(S.tocsc()).solve(b)
+        return x.reshape(rows, cols, K)
+
+    def close(self):
+        pass
+
+
+def test_poisson_composed_host_logic_against_reference_goldens(monkeypatch):
+    """poisson.solve_poisson_simple's composed path (bilaplacian=True, rows over several pixels, constraints on masked-out
+    pixels) with libhgrid replaced by its scipy specification: the host-side transformation reproduces the unmodified
+    reference (tests/golden/reference_poisson.npz, cases of oracle/make_golden_poisson.py: cases2)."""
+    import contextlib
+    import io
+    import poisson_cases as pc
+    from harmonic_interpolation_b200 import poisson as P
+    monkeypatch.setattr(P, "GridSolver", _ScipyComposedSolver)
+    for name in pc.NAMES2:
+        kw, want = pc.load2(name)
+        with contextlib.redirect_stdout(io.StringIO()):
+            got = P.solve_poisson_simple(**kw)
+        tol = 1e-7 if kw["bilaplacian"] else 1e-9
+        assert np.abs(got - want).max() <= tol * max(1.0, np.abs(want).max()), name
+
+
+def test_poisson_components_and_rank_check():
+    """poisson.components against scipy's labelling of the same graph; check_constrained raises exactly when the reference's
+    system matrix is singular."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import connected_components
+    from harmonic_interpolation_b200 import poisson as P
+    rng = np.random.default_rng(2)
+    for trial in range(20):
+        rows, cols = int(rng.integers(1, 14)), int(rng.integers(1, 14))
+        free = rng.random((rows, cols)) < 0.8
+        down = rng.random((rows, cols)) < 0.7; down[-1] = False
+        right = rng.random((rows, cols)) < 0.7; right[:, -1] = False
+        labels, nc = P.components(free, down, right)
+        idx = np.arange(rows * cols).reshape(rows, cols)
+        ed = free[:-1] & free[1:] & down[:-1]
+        er = free[:, :-1] & free[:, 1:] & right[:, :-1]
+        I = np.concatenate([idx[:-1][ed], idx[:, :-1][er]]); J = np.concatenate([idx[1:][ed], idx[:, 1:][er]])
+        g = sp.coo_matrix((np.ones(len(I)), (I, J)), shape=(rows * cols, rows * cols))
+        _, want = connected_components(g, directed=False)
+        f = free.ravel()
+        assert nc == len(np.unique(want[f]))
+        assert (labels.ravel()[~f] == -1).all()
+        # the same partition
+        pairs = set(zip(labels.ravel()[f].tolist(), want[f].tolist()))
+        assert len(pairs) == nc
+    free = np.ones((4, 6), bool); down = np.ones((4, 6), bool); right = np.ones((4, 6), bool)
+    right[:, 2] = False                                   # two components: columns 0..2 and 3..5
+    P.check_constrained(free, down, right, [([0], [1.0], None), ([5], [2.0], None)])
+    P.check_constrained(free, down, right, [([0, 5], [1.0, 1.0], None), ([1, 4], [1.0, -1.0], None)])
+    import pytest
+    with pytest.raises(ArithmeticError):
+        P.check_constrained(free, down, right, [([0], [1.0], None)])                      # the right half floats
+    with pytest.raises(ArithmeticError):
+        P.check_constrained(free, down, right, [([0, 1], [1.0, -1.0], None), ([5], [1.0], None)])   # a difference pins nothing
+    with pytest.raises(ArithmeticError):
+        P.check_constrained(free, down, right, [([0, 5], [1.0, 1.0], None)])               # one row, two constants

@@ -108,3 +108,14 @@ def test_poisson_oracle_matches_reference_golden(name):
     got = go.solve_poisson_simple(kw["target_gradients"], kw["linear_constraints"], kw["linear_constraints_weight"],
                                   kw.get("mask"), kw.get("mask_value"))
     assert np.abs(got - want).max() <= 1e-9 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("name", ["bilap_plain", "bilap_masked", "multi_lap", "multi_bilap", "multi_free_mask", "selftest_small", "selftest_bilap"])
+def test_poisson_oracle_matches_reference_golden_round2(name):
+    """the (G.T G)^2 form (poisson.py:65-67), constraint rows over several pixels (poisson.py:329-366) and constraints on
+    masked-out pixels (poisson.py:419-423), against outputs of the unmodified reference"""
+    import poisson_cases as pc
+    kw, want = pc.load2(name)
+    got = go.solve_poisson_simple(kw["target_gradients"], kw["linear_constraints"], kw["linear_constraints_weight"],
+                                  kw.get("mask"), kw.get("mask_value"), kw["bilaplacian"])
+    assert np.abs(got - want).max() <= (1e-7 if kw["bilaplacian"] else 1e-9) * max(1.0, np.abs(want).max())
