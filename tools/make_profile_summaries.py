@@ -29,8 +29,16 @@ def launch_list(path, out):
         name = re.sub(r'\(.*', '', name)
         d = per.setdefault(r[idc], {'name': name, 'grid': r[gs]})
         d[r[mn]] = float(r[mv].replace(',', ''))
+    # keep the LAST solve only: it starts at the last reset_guess_kernel (set-up and the warm-up solve come before it)
+    order = list(per.values())
+    starts = [i for i, d in enumerate(order) if d['name'].startswith('reset_guess_kernel')]
+    if starts:
+        order = order[starts[-1]:]
+        ends = [i for i, d in enumerate(order) if d['name'].startswith('cg_outer_kernel')]     # the solve ends with its last true-residual stage
+        if ends:
+            order = order[:ends[-1] + 1]
     agg = collections.OrderedDict()
-    for d in per.values():
+    for d in order:
         key = d['name'] + ('  grid ' + d['grid'] if ('cs_leg' in d['name'] or 'cdown' in d['name'] or 'cup_' in d['name']) else '')
         a = agg.setdefault(key, [0, 0.0, 0.0, 0.0])
         a[0] += 1; a[1] += d.get('gpu__time_duration.sum', 0) / 1e6; a[2] += d.get('dram__bytes_read.sum', 0) / 1e9; a[3] += d.get('dram__bytes_write.sum', 0) / 1e9
@@ -54,34 +62,42 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio']
 
 
-def full(path):
+def full(path, match=None):
+    """metrics of the first captured launch whose kernel name contains `match`"""
     rows = list(csv.reader(open(path)))
-    d = dict(zip(rows[0], rows[2]))
     units = dict(zip(rows[0], rows[1]))
-    return d, units
+    for r in rows[2:]:
+        d = dict(zip(rows[0], r))
+        if match is None or match in d.get("Kernel Name", ""):
+            return d, units
+    raise KeyError(match)
 
 
 def main():
-    if os.path.isfile(os.path.join(G, "r2s_launches.csv")):
-        launch_list(os.path.join(G, "r2s_launches.csv"), os.path.join(OUT, "launches_16384_k3_fp32_summary.txt"))
-    caps = [("x/r update+check", "cg_update_tile_kernel<float>", "r2o_cg_update_tile_kernel_raw.csv"),
-            ("fine down", "sl_down_kernel<float, 0, 1> (lean chunks)", "r2o_sl_down_kernel_raw.csv"),
-            ("fine up", "sl_up_kernel<float, 0, 1> (lean chunks)", "r2o_sl_up_kernel_raw.csv"),
-            ("stencil+alpha", "sl_lap_kernel<float, float, 0, 0> (lean chunks)", "r2o_sl_lap_kernel_raw.csv"),
-            ("level-1 down", "cs_leg_kernel<float, 0> level 1 (8192^2)", "r2s_cs_leg_kernel_raw.csv"),
-            ("level-1 up", "cs_leg_kernel<float, 1> level 1 (8192^2)", "r2s_cs_up_raw.csv"),
-            ("beta+p update", "cg_pupdate_tile_kernel<float>", "r2s_cg_pupdate_tile_kernel_raw.csv")]
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r2y"          # tools/gpu_prof3.sh <tag>
+    if os.path.isfile(os.path.join(G, tag + "_launches.csv")):
+        launch_list(os.path.join(G, tag + "_launches.csv"), os.path.join(OUT, "launches_16384_k3_fp32_summary.txt"))
+        import shutil
+        shutil.copy(os.path.join(G, tag + "_launches.csv"), os.path.join(OUT, "launches_16384_k3_fp32.csv"))
+    caps = [("x/r update+check", "cg_update_tile_kernel<float>", tag + "_vec_raw.csv", "cg_update_tile_kernel"),
+            ("fine down", "sl_down_kernel<float, 0, 1> (lean chunks)", tag + "_sl_raw.csv", "sl_down_kernel<float, 0, 1>"),
+            ("fine up", "sl_up_kernel<float, 0, 1> (lean chunks)", tag + "_sl_raw.csv", "sl_up_kernel<float, 0, 1>"),
+            ("stencil+alpha", "sl_lap_kernel<float, float, 0, 0> (lean chunks)", tag + "_sl_raw.csv", "sl_lap_kernel<float, float, 0, 0>"),
+            ("outer residual", "sl_lap_kernel<double, float, 0, 1> (fp64 true residual, lean chunks)", tag + "_sl_raw.csv", "sl_lap_kernel<double, float, 0, 1>"),
+            ("level-1 down", "cs_leg_kernel<float, 0> level 1 (8192^2)", tag + "_csdown_raw.csv", "cs_leg_kernel<float, 0>"),
+            ("level-1 up", "cs_leg_kernel<float, 1> level 1 (8192^2)", tag + "_csup_raw.csv", "cs_leg_kernel<float, 1>"),
+            ("beta+p update", "cg_pupdate_tile_kernel<float>", tag + "_vec_raw.csv", "cg_pupdate_tile_kernel")]
     traffic = {}
     with open(os.path.join(OUT, "ncu_full_summary.csv"), "w", newline="") as f:
         w = csv.writer(f)
         w.writerow(["phase", "kernel", "Kernel Name (ncu)"] + KEYS)
-        for phase, label, fn in caps:
+        for phase, label, fn, match in caps:
             p = os.path.join(G, fn)
             if not os.path.isfile(p) or len(list(csv.reader(open(p)))) < 3:
                 continue
-            d, units = full(p)
+            d, units = full(p, match)
             w.writerow([phase, label, d.get("Kernel Name", "")] + [d.get(k, "") + " " + units.get(k, "") for k in KEYS])
-            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "GB": 1e9, "MB": 1e6, "KB": 1e3, "B": 1.0}
             rd = float(d["dram__bytes_read.sum"]) * scale.get(units["dram__bytes_read.sum"], 1.0)
             wr = float(d["dram__bytes_write.sum"]) * scale.get(units["dram__bytes_write.sum"], 1.0)
             traffic[phase] = {"kernel": label, "dram_read_bytes": rd, "dram_write_bytes": wr,
