@@ -455,6 +455,16 @@ def main():
                             "ms_per_launch": dom["ms_per_launch"], "peak_source": peak_src, "frac_of_8TBs_nominal": dom["achieved_gbs"] / 8000.0,
                             "bytes_basis": "pixels of the 32x64 blocks that hold a free pixel (blocks without one are skipped by every kernel)",
                             "timing": "CUDA events on the solver's stream around the launch inside a real solve (hg_set_phase_timing); includes the one-block scalar stage that follows"}
+    if single:
+        # the kernel furthest below the roofline, and the time-weighted figure over every kernel of the table
+        worst = min(single, key=lambda r: r["frac"])
+        line["roofline_worst"] = {"kernel": worst["kernel"], "share": worst["share"], "frac": worst["frac"], "achieved": worst["achieved_gbs"],
+                                  "unit": "GB/s", "ms_per_launch": worst["ms_per_launch"]}
+        tb = sum(r["algorithmic_bytes_per_launch"] * r["launches"] for r in single)
+        tm = sum(r["ms_total"] for r in single)
+        line["roofline_time_weighted"] = {"achieved": tb / (tm * 1e-3) / 1e9, "unit": "GB/s", "frac": tb / (tm * 1e-3) / 1e9 / peak,
+                                          "share_of_solve": tm / tot_ms,
+                                          "what": "algorithmic bytes of the kernels in `kernels` that carry a byte model / their device time"}
     faulthandler.cancel_dump_traceback_later()
     if not args.no_cpu_baseline:
         u, dt, kind, how = cpu_fill(CPU_SAMPLE_N)

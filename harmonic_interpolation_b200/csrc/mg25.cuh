@@ -29,6 +29,15 @@ struct Lev25 {
     T* coef;   // 25 planes, plane (di + 2) * 5 + (dj + 2); a pixel whose centre coefficient is 0 is inactive
     T* x;      // K planes
     T* b;      // K planes
+    // Colour-major copy of the coefficients for the smoother (round 2): colour (a, b) = (i mod 3, j mod 3) owns the compact
+    // planes coefc[((3 a + b) * 25 + c) * plane3 + (i / 3) * pitch3 + j / 3].  A colour launch of the Gauss-Seidel sweep
+    // reads its coefficients contiguously, every sector once per sweep; out of the pixel-major planes it touched every sector
+    // that holds one of its columns, i.e. every sector in three of the nine launches (3.5x the bytes, ncu round 2).
+    T* coefc;
+    int pitch3;
+    long long plane3;
+    unsigned nz;   // bit c set: plane c holds a non-zero somewhere (level 0: the 13 entries with |di| + |dj| <= 2)
+    T* res;    // K planes: the residual of the level (levels with a coarser one below)
 };
 
 template <typename T>
@@ -136,20 +145,33 @@ galerkin25_kernel(Acc25<T> fine, Lev25<T> cl) {
         for (int b = 0; b < 5; ++b) cl.coef[(a * 5 + b) * cl.plane + oc] = (T)acc[a][b];
 }
 
-// ---- nine-colour Gauss-Seidel, one colour per launch ------------------------------------------------------
+// ---- colour-major copy of a level's coefficients (setup) ---------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(128)
-gs25_kernel(Lev25<T> L, int colour, const int* __restrict__ done) {
-    if (done && *done) return;
-    const int i = 3 * blockIdx.y + colour / 3;
-    const int j = 3 * (blockIdx.x * blockDim.x + threadIdx.x) + colour % 3;
+colour_pack25_kernel(Lev25<T> L) {
+    const int j3 = blockIdx.x * blockDim.x + threadIdx.x, i3 = blockIdx.y, colour = blockIdx.z;
+    if (j3 >= L.pitch3) return;
+    const int i = 3 * i3 + colour / 3, j = 3 * j3 + colour % 3;
+    const bool in = i < L.rows && j < L.cols;
+    const long long o = (long long)i * L.pitch + j, oc = (long long)i3 * L.pitch3 + j3;
+    for (int c = 0; c < 25; ++c)
+        if ((L.nz >> c) & 1u) L.coefc[((long long)colour * 25 + c) * L.plane3 + oc] = in ? L.coef[c * L.plane + o] : T(0);
+}
+
+// ---- nine-colour Gauss-Seidel ---------------------------------------------------------------------------------
+// update of pixel (3 i3 + colour / 3, 3 j3 + colour % 3), every channel
+template <typename T>
+__device__ __forceinline__ void gs25_pixel(const Lev25<T>& L, int colour, int i3, int j3) {
+    const int i = 3 * i3 + colour / 3;
+    const int j = 3 * j3 + colour % 3;
     if (i >= L.rows || j >= L.cols) return;
     const long long o = (long long)i * L.pitch + j;
-    const T c12 = L.coef[12 * L.plane + o];
+    const T* __restrict__ cc = L.coefc + (long long)colour * 25 * L.plane3 + ((long long)i3 * L.pitch3 + j3);
+    const T c12 = cc[12 * L.plane3];
     if (!(c12 > T(0))) return;
     T cf[25];
 #pragma unroll
-    for (int c = 0; c < 25; ++c) cf[c] = c == 12 ? c12 : L.coef[c * L.plane + o];
+    for (int c = 0; c < 25; ++c) cf[c] = c == 12 ? c12 : (((L.nz >> c) & 1u) ? cc[c * L.plane3] : T(0));
     const T inv = T(1) / c12;
     for (int k = 0; k < L.K; ++k) {
         T* xk = L.x + k * L.plane;
@@ -164,11 +186,64 @@ gs25_kernel(Lev25<T> L, int colour, const int* __restrict__ done) {
         xk[o] = v * inv;
     }
 }
-
-// ---- residual + restriction:  b_c = P^T (b_f - A_f x_f),  x_c = 0 ------------------------------------------
+// one colour per launch (large levels)
 template <typename T>
 __global__ void __launch_bounds__(128)
-resid_restrict25_kernel(Lev25<T> F, Lev25<T> cl, const int* __restrict__ done) {
+gs25_kernel(Lev25<T> L, int colour, const int* __restrict__ done) {
+    if (done && *done) return;
+    gs25_pixel(L, colour, (int)blockIdx.y, (int)(blockIdx.x * blockDim.x + threadIdx.x));
+}
+// Small levels: `sweeps` whole sweeps in ONE launch of one block, a block barrier between colours (nine launches of a few
+// blocks each cost ~8 us apiece, all of it latency: 54 launches per V-cycle on the levels of 128^2 pixels and below).
+#define GS25_SMALL_PIXELS 16384
+template <typename T>
+__global__ void __launch_bounds__(1024)
+gs25_small_kernel(Lev25<T> L, int forward, int sweeps, const int* __restrict__ done) {
+    if (done && *done) return;
+    const int r3 = (L.rows + 2) / 3, c3 = (L.cols + 2) / 3;
+    for (int s = 0; s < sweeps; ++s)
+        for (int q = 0; q < 9; ++q) {
+            const int colour = forward ? q : 8 - q;
+            for (int e = threadIdx.x; e < r3 * c3; e += blockDim.x) gs25_pixel(L, colour, e / c3, e % c3);
+            __syncthreads();      // (also orders the block's global writes for its own later reads)
+        }
+}
+
+// ---- residual + restriction:  b_c = P^T (b_f - A_f x_f),  x_c = 0 ------------------------------------------
+// Two passes (round 2): the residual once per fine pixel (coalesced reads of the coefficient planes that hold non-zeros),
+// then full weighting of the stored residual.  The one-pass form evaluated the residual of a fine pixel for each of its
+// up to four coarse parents (1.8x the coefficient bytes from DRAM at 4096^2).  Same arithmetic, same order: same bits.
+template <typename T>
+__global__ void __launch_bounds__(128)
+resid25_kernel(Lev25<T> F, const int* __restrict__ done) {
+    if (done && *done) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= F.pitch) return;
+    const long long o = (long long)i * F.pitch + j;
+    const bool live = j < F.cols && F.coef[12 * F.plane + o] != T(0);
+    T cf[25];
+#pragma unroll
+    for (int c = 0; c < 25; ++c) cf[c] = (live && ((F.nz >> c) & 1u)) ? F.coef[c * F.plane + o] : T(0);
+    for (int k = 0; k < F.K; ++k) {
+        T res = T(0);
+        if (live) {
+            const T* xk = F.x + k * F.plane;
+            res = F.b[k * F.plane + o];
+#pragma unroll
+            for (int di = -2; di <= 2; ++di)
+#pragma unroll
+                for (int dj = -2; dj <= 2; ++dj) {
+                    const int c = (di + 2) * 5 + (dj + 2);
+                    if (cf[c] != T(0)) res -= cf[c] * xk[o + (long long)di * F.pitch + dj];
+                }
+        }
+        F.res[k * F.plane + o] = res;
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(128)
+restrict25_kernel(Lev25<T> F, Lev25<T> cl, const int* __restrict__ done) {
     if (done && *done) return;
     const int J = blockIdx.x * blockDim.x + threadIdx.x;
     const int I = blockIdx.y;
@@ -178,8 +253,7 @@ resid_restrict25_kernel(Lev25<T> F, Lev25<T> cl, const int* __restrict__ done) {
     for (int k = 0; k < F.K; ++k) {
         double s = 0.0;
         if (live) {
-            const T* xk = F.x + k * F.plane;
-            const T* bk = F.b + k * F.plane;
+            const T* rk = F.res + k * F.plane;
             for (int a = -1; a <= 1; ++a) {
                 const double wa = w1d(a, I, F.rows, cl.rows);
                 if (wa == 0.0) continue;
@@ -190,15 +264,7 @@ resid_restrict25_kernel(Lev25<T> F, Lev25<T> cl, const int* __restrict__ done) {
                     if (pi < 0 || pi >= F.rows || pj < 0 || pj >= F.cols) continue;
                     const long long o = (long long)pi * F.pitch + pj;
                     if (F.coef[12 * F.plane + o] == T(0)) continue;
-                    T res = bk[o];
-#pragma unroll
-                    for (int di = -2; di <= 2; ++di)
-#pragma unroll
-                        for (int dj = -2; dj <= 2; ++dj) {
-                            const T cf = F.coef[((di + 2) * 5 + (dj + 2)) * F.plane + o];
-                            if (cf != T(0)) res -= cf * xk[o + (long long)di * F.pitch + dj];
-                        }
-                    s += wp * (double)res;
+                    s += wp * (double)rk[o];
                 }
             }
         }

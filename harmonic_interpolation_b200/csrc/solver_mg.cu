@@ -13,7 +13,7 @@ void Solver<T>::free_hierarchy() {
     dfree(d_dense); dfree(d_gdense);
     d_dense = d_gdense = nullptr;
     for (size_t l = 0; l < lev25.size(); ++l) {
-        dfree(lev25[l].coef);
+        dfree(lev25[l].coef); dfree(lev25[l].coefc); dfree(lev25[l].res);
         if (l > 0) { dfree(lev25[l].x); dfree(lev25[l].b); }
     }
     lev25.clear();

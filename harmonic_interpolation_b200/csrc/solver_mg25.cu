@@ -18,8 +18,15 @@ int Solver<T>::build_hierarchy25() {
         L.pitch = level == 0 ? pitch : round_up(c, 32);
         L.plane = (long long)L.rows * L.pitch;
         L.K = K;
-        L.coef = L.x = L.b = nullptr;
+        L.coef = L.x = L.b = L.coefc = L.res = nullptr;
+        L.pitch3 = round_up((L.cols + 2) / 3, 32);
+        L.plane3 = (long long)((L.rows + 2) / 3) * L.pitch3;
+        L.nz = 0u;
+        for (int di = -2; di <= 2; ++di)
+            for (int dj = -2; dj <= 2; ++dj)
+                if (level > 0 || abs(di) + abs(dj) <= 2) L.nz |= 1u << ((di + 2) * 5 + (dj + 2));     // L^T L couples |di| + |dj| <= 2
         CU(dmalloc(&L.coef, (size_t)L.plane * 25 * sizeof(T)));
+        CU(dmalloc(&L.coefc, (size_t)L.plane3 * 9 * 25 * sizeof(T)));
         if (level > 0) {
             CU(dmalloc(&L.x, (size_t)L.plane * K * sizeof(T)));
             CU(dmalloc(&L.b, (size_t)L.plane * K * sizeof(T)));
@@ -29,8 +36,11 @@ int Solver<T>::build_hierarchy25() {
         dim3 cg((L.pitch + 127) / 128, L.rows);
         if (level == 0) assemble25_kernel<T><<<cg, 128, 0, stream>>>(grid(), L);
         else galerkin25_kernel<T><<<cg, 128, 0, stream>>>(Acc25<T>{lev25.back()}, L);
+        colour_pack25_kernel<T><<<dim3((L.pitch3 + 127) / 128, (L.rows + 2) / 3, 9), 128, 0, stream>>>(L);
+        const bool last = (long long)r * c <= 256;
+        if (!last) CU(dmalloc(&L.res, (size_t)L.plane * K * sizeof(T)));
         lev25.push_back(L);
-        if ((long long)r * c <= 256) break;
+        if (last) break;
         r = (r + 1) / 2; c = (c + 1) / 2;
     }
     const Lev25<T>& L = lev25.back();
@@ -45,6 +55,11 @@ int Solver<T>::build_hierarchy25() {
 
 template <typename T>
 void Solver<T>::gs25(Lev25<T>& L, bool forward, const int* done) {
+    if ((long long)L.rows * L.cols <= GS25_SMALL_PIXELS) {
+        gs25_small_kernel<T><<<1, 1024, 0, stream>>>(L, forward ? 1 : 0, mg25_sweeps, done);
+        ++launches;
+        return;
+    }
     dim3 gg(((L.cols + 2) / 3 + 127) / 128, (L.rows + 2) / 3);
     for (int s = 0; s < mg25_sweeps; ++s)
         for (int c = 0; c < 9; ++c) gs25_kernel<T><<<gg, 128, 0, stream>>>(L, forward ? c : 8 - c, done);
@@ -60,7 +75,8 @@ int Solver<T>::vcycle25(T* z, T* r, const int* done) {
     for (int l = 0; l + 1 < n; ++l) {
         gs25(lev25[l], true, done);
         const Lev25<T>& Lc = lev25[l + 1];
-        resid_restrict25_kernel<T><<<dim3((Lc.pitch + 127) / 128, Lc.rows), 128, 0, stream>>>(lev25[l], Lc, done);
+        resid25_kernel<T><<<dim3((lev25[l].pitch + 127) / 128, lev25[l].rows), 128, 0, stream>>>(lev25[l], done);
+        restrict25_kernel<T><<<dim3((Lc.pitch + 127) / 128, Lc.rows), 128, 0, stream>>>(lev25[l], Lc, done);
     }
     const Lev25<T>& Lb = lev25[n - 1];
     coarsest_dense25_kernel<T><<<K, 256, Lb.rows * Lb.cols * sizeof(double), stream>>>(Lb, d_dense25, done);
@@ -68,7 +84,7 @@ int Solver<T>::vcycle25(T* z, T* r, const int* done) {
         prolong_add25_kernel<T><<<dim3((lev25[l].cols + 255) / 256, lev25[l].rows), 256, 0, stream>>>(lev25[l], lev25[l + 1], done);
         gs25(lev25[l], false, done);
     }
-    launches += 2 * (n - 1) + 2;
+    launches += 3 * (n - 1) + 2;
     return HG_OK;
 }
 

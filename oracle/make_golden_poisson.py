@@ -52,7 +52,8 @@ def cases2():
     for name, rows, cols, K, bilap, multi, kind in (("bilap_plain", 26, 33, 1, True, False, None), ("bilap_masked", 30, 26, 2, True, False, "value"),
                                                     ("multi_lap", 21, 28, 2, False, True, None), ("multi_bilap", 24, 24, 1, True, True, "value"),
                                                     ("multi_free_mask", 20, 23, 1, False, True, "free"),
-                                                    ("selftest_small", 36, 36, 1, False, False, "selftest"), ("selftest_bilap", 36, 36, 1, True, False, "selftest")):
+                                                    ("selftest_small", 36, 36, 1, False, False, "selftest"), ("selftest_bilap", 36, 36, 1, True, False, "selftest"),
+                                                    ("row_bilap", 1, 9, 1, True, False, None), ("tiny_multi", 3, 2, 2, True, True, None)):
         u = rng.normal(size=(rows, cols, 2, K))
         mask = mask_value = None
         ent, vals = [], []

@@ -7,7 +7,8 @@ import numpy as np
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_poisson.npz")
 NAMES = ("plain", "rgb", "masked", "island")
 # round 2: (G.T G)^2, constraint rows over several pixels, constraints on masked-out pixels (oracle/make_golden_poisson.py: cases2)
-NAMES2 = ("bilap_plain", "bilap_masked", "multi_lap", "multi_bilap", "multi_free_mask", "selftest_small", "selftest_bilap")
+NAMES2 = ("bilap_plain", "bilap_masked", "multi_lap", "multi_bilap", "multi_free_mask", "selftest_small", "selftest_bilap",
+          "row_bilap", "tiny_multi")
 
 
 def load(name):

@@ -110,7 +110,7 @@ def test_poisson_oracle_matches_reference_golden(name):
     assert np.abs(got - want).max() <= 1e-9 * max(1.0, np.abs(want).max())
 
 
-@pytest.mark.parametrize("name", ["bilap_plain", "bilap_masked", "multi_lap", "multi_bilap", "multi_free_mask", "selftest_small", "selftest_bilap"])
+@pytest.mark.parametrize("name", ["bilap_plain", "bilap_masked", "multi_lap", "multi_bilap", "multi_free_mask", "selftest_small", "selftest_bilap", "row_bilap", "tiny_multi"])
 def test_poisson_oracle_matches_reference_golden_round2(name):
     """the (G.T G)^2 form (poisson.py:65-67), constraint rows over several pixels (poisson.py:329-366) and constraints on
     masked-out pixels (poisson.py:419-423), against outputs of the unmodified reference"""
