@@ -224,9 +224,10 @@ struct Solver : SolverBase {
     // exchanges r (level 0, 128 rows), gathers level 5 and refreshes level 4 once; HGRID_EXCHANGE_ALL=1 restores a refresh per
     // level and leg (8 more send / recv groups per cycle).  tests/dist_check.py holds both to the single-GPU answer.
     bool exchange_all = getenv("HGRID_EXCHANGE_ALL") != nullptr;
-    // HGRID_OVERLAP=1 (slab mode; written after round 1's GPU budget was spent, NOT YET RUN on a GPU -- off by default):
-    // the 128-row exchange of r at the head of the V-cycle travels on a second stream while the downward leg works
-    // on the chunks that read no ghost row; the chunks next to the ghost bands follow once the rows have arrived.
+    // HGRID_OVERLAP=1 (slab mode; off by default): the 128-row exchange of r at the head of the V-cycle travels on a second
+    // stream while the downward leg works on the chunks that read no ghost row; the chunks next to the ghost bands follow
+    // once the rows have arrived.  Run in round 2 on 4 GPUs: exact (profiles/r2/dist_check_world4_overlap.log), 74.9 vs
+    // 74.5 ms -- the exchange costs less than the split launch saves, so it stays an option.
     bool overlap = getenv("HGRID_OVERLAP") != nullptr;
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_arrived = nullptr;
