@@ -186,27 +186,23 @@ __device__ __forceinline__ void gs25_pixel(const Lev25<T>& L, int colour, int i3
         xk[o] = v * inv;
     }
 }
-// one colour per launch (large levels)
+// One launch per ROW colour a = i mod 3, one block per row: the three column colours of the row follow each other inside
+// the block with a block barrier in between (rows 3 apart are not coupled by a 5 x 5 stencil, so blocks never wait for each
+// other).  Same order as nine launches -- colours 3 a + 0, 1, 2, then the next a -- so the same iterates; but three launches
+// per sweep instead of nine (the levels <= 512^2 are launch-latency-bound), and the row's b and the five rows of x under the
+// stencil are fetched from DRAM once per row colour instead of once per colour (they were half of the smoother's traffic
+// on level 0 once the coefficients were colour-major).
+#define GS25_ROW_THREADS 512
 template <typename T>
-__global__ void __launch_bounds__(128)
-gs25_kernel(Lev25<T> L, int colour, const int* __restrict__ done) {
+__global__ void __launch_bounds__(GS25_ROW_THREADS)
+gs25_rows_kernel(Lev25<T> L, int a, int forward, const int* __restrict__ done) {
     if (done && *done) return;
-    gs25_pixel(L, colour, (int)blockIdx.y, (int)(blockIdx.x * blockDim.x + threadIdx.x));
-}
-// Small levels: `sweeps` whole sweeps in ONE launch of one block, a block barrier between colours (nine launches of a few
-// blocks each cost ~8 us apiece, all of it latency: 54 launches per V-cycle on the levels of 128^2 pixels and below).
-#define GS25_SMALL_PIXELS 16384
-template <typename T>
-__global__ void __launch_bounds__(1024)
-gs25_small_kernel(Lev25<T> L, int forward, int sweeps, const int* __restrict__ done) {
-    if (done && *done) return;
-    const int r3 = (L.rows + 2) / 3, c3 = (L.cols + 2) / 3;
-    for (int s = 0; s < sweeps; ++s)
-        for (int q = 0; q < 9; ++q) {
-            const int colour = forward ? q : 8 - q;
-            for (int e = threadIdx.x; e < r3 * c3; e += blockDim.x) gs25_pixel(L, colour, e / c3, e % c3);
-            __syncthreads();      // (also orders the block's global writes for its own later reads)
-        }
+    const int i3 = blockIdx.x, c3 = (L.cols + 2) / 3;
+    for (int q = 0; q < 3; ++q) {
+        const int colour = 3 * a + (forward ? q : 2 - q);
+        for (int j3 = threadIdx.x; j3 < c3; j3 += blockDim.x) gs25_pixel(L, colour, i3, j3);
+        __syncthreads();          // (also orders the block's global writes for its own later reads)
+    }
 }
 
 // ---- residual + restriction:  b_c = P^T (b_f - A_f x_f),  x_c = 0 ------------------------------------------

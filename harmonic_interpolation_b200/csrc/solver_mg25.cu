@@ -55,15 +55,11 @@ int Solver<T>::build_hierarchy25() {
 
 template <typename T>
 void Solver<T>::gs25(Lev25<T>& L, bool forward, const int* done) {
-    if ((long long)L.rows * L.cols <= GS25_SMALL_PIXELS) {
-        gs25_small_kernel<T><<<1, 1024, 0, stream>>>(L, forward ? 1 : 0, mg25_sweeps, done);
-        ++launches;
-        return;
-    }
-    dim3 gg(((L.cols + 2) / 3 + 127) / 128, (L.rows + 2) / 3);
+    const int c3 = (L.cols + 2) / 3;
+    const int threads = std::min(GS25_ROW_THREADS, round_up(c3, 32));
     for (int s = 0; s < mg25_sweeps; ++s)
-        for (int c = 0; c < 9; ++c) gs25_kernel<T><<<gg, 128, 0, stream>>>(L, forward ? c : 8 - c, done);
-    launches += 9 * mg25_sweeps;
+        for (int q = 0; q < 3; ++q) gs25_rows_kernel<T><<<(L.rows + 2) / 3, threads, 0, stream>>>(L, forward ? q : 2 - q, forward ? 1 : 0, done);
+    launches += 3 * mg25_sweeps;
 }
 
 // z = M^-1 r: one symmetric V-cycle from the zero guess on the 25-point hierarchy (level 0 works in place on z, r)
