@@ -131,6 +131,7 @@ int Solver<T>::solve_device_impl(double rtol, int maxiter, hg_stats* st) {
         mark(HG_PH_OUTER);
         CU(cudaMemcpyAsync(&host, d_state, sizeof host, cudaMemcpyDeviceToHost, stream));
         HGTRY(sync_watchful());
+        if (phase_print) fprintf(stderr, "[hgrid] outer pass %d: true relres %.3e after %d iterations\n", outer, sqrt(host.outer_ratio), host.iter);
         if (host.done) break;                                   // converged (1), NaN (2) or out of iterations (4)
         if (outer >= max_outer) break;
         // a refinement step that did not gain a factor 4 has hit the attainable accuracy
