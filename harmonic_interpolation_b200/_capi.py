@@ -66,6 +66,8 @@ SYMBOLS = {
                                          ctypes.POINTER(Stats)]),
     "hg_solve_u8": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_uint8), ctypes.c_double, ctypes.c_int, ctypes.POINTER(Stats)]),
     "hg_upload_values": (ctypes.c_int, [_H, ctypes.POINTER(Values), ctypes.POINTER(Stats)]),
+    "hg_upload_values_sparse": (ctypes.c_int, [_H, ctypes.c_longlong, ctypes.POINTER(ctypes.c_longlong), _dp, ctypes.c_longlong,
+                                               ctypes.POINTER(ctypes.c_longlong), _dp, ctypes.POINTER(Stats)]),
     "hg_solve_device": (ctypes.c_int, [_H, ctypes.c_double, ctypes.c_int, ctypes.POINTER(Stats)]),
     "hg_download": (ctypes.c_int, [_H, _dp, ctypes.POINTER(Stats)]),
     "hg_reset_guess": (ctypes.c_int, [_H]),

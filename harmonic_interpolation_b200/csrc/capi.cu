@@ -121,6 +121,11 @@ int hg_set_edge_weights(hg_handle h, int mode) { CHECK_H(h); return h->impl->set
 int hg_setup(hg_handle h, hg_setup_info* info) { CHECK_H(h); return h->impl->setup(info); }
 int hg_apply(hg_handle h, const double* x, double* y) { CHECK_H(h); return h->impl->apply(x, y); }
 int hg_upload_values(hg_handle h, const hg_values* v, hg_stats* st) { CHECK_H(h); return h->impl->upload(v, st); }
+int hg_upload_values_sparse(hg_handle h, long long n_hard, const long long* hard_idx, const double* hard_vals, long long n_soft,
+                            const long long* soft_idx, const double* soft_vals, hg_stats* st) {
+    CHECK_H(h);
+    return h->impl->upload_sparse(n_hard, hard_idx, hard_vals, n_soft, soft_idx, soft_vals, st);
+}
 int hg_solve_device(hg_handle h, double rtol, int maxiter, hg_stats* st) { CHECK_H(h); return h->impl->solve_device(rtol, maxiter, st); }
 int hg_download(hg_handle h, double* x, hg_stats* st) { CHECK_H(h); return h->impl->download(x, st); }
 int hg_bench_apply(hg_handle h, int iters, double* ms) { CHECK_H(h); return h->impl->bench_apply(iters, ms); }

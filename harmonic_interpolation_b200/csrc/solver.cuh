@@ -116,6 +116,7 @@ struct SolverBase {
     virtual int setup(hg_setup_info* info) = 0;
     virtual int apply(const double* x, double* y) = 0;
     virtual int upload(const hg_values* v, hg_stats* st) = 0;
+    virtual int upload_sparse(long long nh, const long long* hidx, const double* hv, long long ns, const long long* sidx, const double* sv, hg_stats* st) = 0;
     virtual int solve_device(double rtol, int maxiter, hg_stats* st) = 0;
     virtual int solve_composed(const hg_linear_constraints* lc, double rtol, int maxiter, hg_stats* st) = 0;
     virtual int download(double* x, hg_stats* st) = 0;
@@ -454,6 +455,7 @@ struct Solver : SolverBase {
     void apply_op(const T* x, T* y);
     int apply(const double* x, double* y) override;
     int upload(const hg_values* v, hg_stats* st) override;
+    int upload_sparse(long long nh, const long long* hidx, const double* hv, long long ns, const long long* sidx, const double* sv, hg_stats* st) override;
 
     // Slab mode.  The local grid is [ghost band | owned rows | ghost band]; ghost bands are
     // HG_GHOST_ROWS deep MIRRORS of the neighbouring slabs (same flags, same values after a

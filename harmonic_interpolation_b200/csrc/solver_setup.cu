@@ -377,6 +377,58 @@ int Solver<T>::upload(const hg_values* v, hg_stats* st) {
     return HG_OK;
 }
 
+// values of the hard / soft constraints as compact lists: scattered into the staging planes on the device
+static __global__ void scatter_values_kernel(const long long* __restrict__ idx, const double* __restrict__ vals, long long n, int K,
+                                             double* __restrict__ dense) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * K) return;
+    const long long e = t / K;
+    dense[idx[e] * K + (t - e * K)] = vals[t];
+}
+
+template <typename T>
+int Solver<T>::upload_sparse(long long nh, const long long* hidx, const double* hv, long long ns, const long long* sidx, const double* sv,
+                             hg_stats* st) {
+    if (!is_setup) return fail(HG_ERR_INVALID, "hg_upload_values_sparse: hg_setup has not been called");
+    if (nh < 0 || ns < 0 || (nh > 0 && (!hidx || !hv)) || (ns > 0 && (!sidx || !sv))) return fail(HG_ERR_INVALID, "hg_upload_values_sparse: bad arguments");
+    const long long npix = (long long)rows * cols;
+    for (long long e = 0; e < nh; ++e) if (hidx[e] < 0 || hidx[e] >= npix) return fail(HG_ERR_INVALID, "hg_upload_values_sparse: pixel index outside the grid");
+    for (long long e = 0; e < ns; ++e) if (sidx[e] < 0 || sidx[e] >= npix) return fail(HG_ERR_INVALID, "hg_upload_values_sparse: pixel index outside the grid");
+    CU(cudaEventRecord(ev0, stream));
+    const size_t bytes = (size_t)npix * K * sizeof(double);
+    long long* d_idx = nullptr; double* d_val = nullptr;
+    const long long nmax = std::max(nh, ns);
+    if (nmax > 0) {
+        CU(dmalloc(&d_idx, (size_t)nmax * sizeof(long long)));
+        CU(dmalloc(&d_val, (size_t)nmax * K * sizeof(double)));
+    }
+    const long long n_of[2] = {nh, ns};
+    const long long* idx_of[2] = {hidx, sidx};
+    const double* val_of[2] = {hv, sv};
+    for (int slot = 0; slot < 2; ++slot) {
+        const long long n = n_of[slot];
+        if (n == 0) continue;
+        if (!d_stage[slot]) CU(dmalloc(&d_stage[slot], bytes));
+        CU(cudaMemsetAsync(d_stage[slot], 0, bytes, stream));
+        CU(cudaMemcpyAsync(d_idx, idx_of[slot], (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpyAsync(d_val, val_of[slot], (size_t)n * K * sizeof(double), cudaMemcpyHostToDevice, stream));
+        scatter_values_kernel<<<(unsigned)((n * K + 255) / 256), 256, 0, stream>>>(d_idx, d_val, n, K, d_stage[slot]);
+    }
+    b_is_zero = ns == 0;
+    dim3 pg((pitch + 255) / 256, rows);
+    build_problem_kernel<T, double><<<pg, 256, 0, stream>>>(grid(), nh ? d_stage[0] : nullptr, ns ? d_stage[1] : nullptr, nullptr, nullptr,
+                                                           nullptr, nullptr, d_xm, d_bm);
+    CU(cudaEventRecord(ev1, stream));
+    CU(cudaStreamSynchronize(stream));
+    CU(cudaGetLastError());
+    dfree(d_idx); dfree(d_val);
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ev0, ev1));
+    if (st) st->upload_ms = ms;
+    have_values = true;
+    return HG_OK;
+}
+
 template <typename T>
 int Solver<T>::upload_u8(const uint8_t* vals, hg_stats* st) {
     if (!is_setup) return fail(HG_ERR_INVALID, "hg_solve_u8: hg_setup has not been called");

@@ -389,6 +389,14 @@ def solve_grid_linear_simple3_solver(rows, cols, value_constraints_hard=[], valu
         dims = set(v.shape[1] for v, i in ((hv, hidx), (sv, sidx)) if len(i))
         assert len(dims) == 1
         K = dims.pop()
+        if K <= 16:
+            # the values go to the device as lists and are scattered there (hg_upload_values_sparse): no dense planes on the host
+            s = solvers.get(K)
+            if s is None:
+                s = GridSolver(rows, cols, K, bilaplacian, precision)
+                s.set_pattern(flags, sw, ss, 0.0)
+                solvers[K] = s
+            return s.solve_sparse(hidx, hv if len(hidx) else None, sidx, sv if len(sidx) else None, rtol=rtol, maxiter=maxiter)
         return _solve_channels(rows, cols, K, bilaplacian, precision, flags, sw, ss, 0.0,
                                dict(hard_vals=_scatter(rows, cols, K, hidx, hv) if len(hidx) else None,
                                     soft_vals=_scatter(rows, cols, K, sidx, sv) if len(sidx) else None),

@@ -160,6 +160,49 @@ class GridSolver:
             C.check(code)
         return out
 
+    def _finish(self, code, stats, allow_unconverged=False):
+        """Error mapping shared by the solve entry points (see `solve`)."""
+        if code == C.ERR_BREAKDOWN:
+            raise ArithmeticError(C.last_error())
+        if code == C.ERR_NOT_CONVERGED:
+            ok = allow_unconverged or os.environ.get("HGRID_ALLOW_UNCONVERGED") or stats.relres <= accept_relres(self.precision)
+            if not ok:
+                raise ArithmeticError("%s (relative residual %.3e after %d iterations)" % (
+                    C.last_error(), stats.relres, stats.iterations))
+        else:
+            C.check(code)
+
+    def solve_sparse(self, hard_idx=None, hard_vals=None, soft_idx=None, soft_vals=None, rtol=None, maxiter=None,
+                     allow_unconverged=False):
+        """`solve` for value constraints given as lists -- row-major pixel indices (unique) and (n, K) values, the form the
+        factor-once closure of recovery.py:1304-1336 is called with: the values are scattered on the device
+        (hg_upload_values_sparse) instead of the caller filling dense (rows, cols, K) planes."""
+        def pack(idx, vals):
+            if idx is None or len(idx) == 0:
+                return 0, None, None
+            idx = np.ascontiguousarray(idx, dtype=np.int64).ravel()
+            vals = np.ascontiguousarray(vals, dtype=np.float64).reshape(len(idx), self.K)
+            return len(idx), idx, vals
+        nh, hi, hv = pack(hard_idx, hard_vals)
+        ns, si, sv = pack(soft_idx, soft_vals)
+        lp = ctypes.POINTER(ctypes.c_longlong)
+        ip = lambda a: ctypes.cast(None, lp) if a is None else a.ctypes.data_as(lp)  # noqa: E731
+        stats = C.Stats()
+        C.check(self._lib.hg_upload_values_sparse(self._h, nh, ip(hi), C.dptr(hv), ns, ip(si), C.dptr(sv), ctypes.byref(stats)))
+        if rtol is None:
+            rtol = default_rtol(self.precision)
+        if maxiter is None:
+            maxiter = int(os.environ.get("HGRID_MAXITER", 0)) or max(2000, 40 * (self.rows + self.cols))
+        code = self._lib.hg_solve_device(self._h, float(rtol), int(maxiter), ctypes.byref(stats))
+        self.last_stats = stats.as_dict()
+        if code != C.ERR_NOT_CONVERGED:
+            self._finish(code, stats)
+        out = np.empty((self.rows, self.cols, self.K), np.float64)
+        C.check(self._lib.hg_download(self._h, C.dptr(out), ctypes.byref(stats)))
+        self.last_stats = stats.as_dict()
+        self._finish(code, stats, allow_unconverged)
+        return out
+
     def solve_composed(self, constraints, weight, squared=False, hard_vals=None, rhs=None, x0=None, rtol=None, maxiter=None,
                        accept=None):
         """(L^m + weight A^T A) x = L^(m-1) rhs + weight A^T c (hg_solve_composed; poisson.py:55-89), m = 2 if `squared`.

@@ -170,6 +170,12 @@ int hg_solve_u8(hg_handle h, const uint8_t* hard_vals, uint8_t* out, double rtol
 
 /* The same in three steps, so that a benchmark can time the device-resident solve. */
 int hg_upload_values(hg_handle h, const hg_values* vals, hg_stats* stats);
+/* List form of hg_upload_values for the factor-once closure (recovery.py:1304-1336), which is called with the VALUES of the
+ * hard / soft constraints whose positions were fixed at construction: row-major pixel indices i * cols + j (unique) and
+ * (n, K) values; the library scatters them on the device instead of the caller filling (rows, cols, K) planes.  Gradient
+ * values, initial guess and explicit right-hand side are taken as absent.  Follow with hg_solve_device + hg_download. */
+int hg_upload_values_sparse(hg_handle h, long long n_hard, const long long* hard_idx, const double* hard_vals,
+                            long long n_soft, const long long* soft_idx, const double* soft_vals, hg_stats* stats);
 int hg_solve_device(hg_handle h, double rtol, int maxiter, hg_stats* stats);
 int hg_download(hg_handle h, double* x_out, hg_stats* stats);
 /* Sets the device-resident iterate back to the zero guess on the free pixels (hard values
