@@ -130,7 +130,10 @@ def _scalar_constraints(cons, rows, cols, i_hi, j_hi):
     assert ((ij[:, 0] >= 0) & (ij[:, 0] < i_hi)).all()
     assert ((ij[:, 1] >= 0) & (ij[:, 1] < j_hi)).all()
     idx = ij[:, 0] * cols + ij[:, 1]
-    assert len(np.unique(idx)) == len(idx)
+    # no pixel twice (a mark per pixel instead of sorting the indices)
+    seen = np.zeros(rows * cols, bool)
+    seen[idx] = True
+    assert int(np.count_nonzero(seen)) == len(idx)
     return idx, vals
 
 
@@ -171,7 +174,10 @@ def _vector_constraints(cons, rows, cols):
     assert ((ij[:, 0] >= 0) & (ij[:, 0] < rows)).all()
     assert ((ij[:, 1] >= 0) & (ij[:, 1] < cols)).all()
     idx = ij[:, 0] * cols + ij[:, 1]
-    assert len(np.unique(idx)) == len(idx)
+    # no pixel twice (a mark per pixel instead of sorting the indices)
+    seen = np.zeros(rows * cols, bool)
+    seen[idx] = True
+    assert int(np.count_nonzero(seen)) == len(idx)
     return idx, vals
 
 
@@ -186,7 +192,10 @@ def _index_constraints(cons, rows, cols):
     assert ((ij[:, 0] >= 0) & (ij[:, 0] < rows)).all()
     assert ((ij[:, 1] >= 0) & (ij[:, 1] < cols)).all()
     idx = ij[:, 0] * cols + ij[:, 1]
-    assert len(np.unique(idx)) == len(idx)
+    # no pixel twice (a mark per pixel instead of sorting the indices)
+    seen = np.zeros(rows * cols, bool)
+    seen[idx] = True
+    assert int(np.count_nonzero(seen)) == len(idx)
     return idx
 
 
