@@ -227,7 +227,8 @@ int Solver<T>::solve_composed(const hg_linear_constraints* lc, double rtol, int 
         };
         auto any_nan = [&](const double* v) { for (int k = 0; k < K; ++k) if (!(v[k] == v[k])) return true; return false; };
 
-        for (int pass = 0; pass < 6 && status == HG_ERR_NOT_CONVERGED; ++pass) {
+        const int max_pass = 6;      // (the last pass only evaluates the true residual of what the one before it left)
+        for (int pass = 0; pass <= max_pass && status == HG_ERR_NOT_CONVERGED; ++pass) {
             // true residual r = b - A x
             op_apply(x, d_q);
             cresid_kernel<<<vg, 256, 0, stream>>>(plane, b, d_q, d_r, cpart);
@@ -238,7 +239,7 @@ int Solver<T>::solve_composed(const hg_linear_constraints* lc, double rtol, int 
             relres = sqrt(now);
             if (now <= tol2) { status = HG_OK; break; }
             if (pass > 0 && !(now < 0.0625 * prev_true)) break;      // a restart that gains less than a factor 4: attainable accuracy
-            if (iter >= maxiter) break;
+            if (iter >= maxiter || pass == max_pass) break;
             prev_true = now;
             if ((rc = precond(d_r, d_z)) != HG_OK) break;
             if ((rc = dot(d_r, d_z, rz)) != HG_OK) break;
