@@ -192,6 +192,16 @@ __device__ __forceinline__ void gs25_pixel(const Lev25<T>& L, int colour, int i3
 // per sweep instead of nine (the levels <= 512^2 are launch-latency-bound), and the row's b and the five rows of x under the
 // stencil are fetched from DRAM once per row colour instead of once per colour (they were half of the smoother's traffic
 // on level 0 once the coefficients were colour-major).
+// one colour per launch, one pixel per thread: on the largest levels nine launches of many small blocks keep more loads in
+// flight than three launches of one 512-thread block per row (ncu, level 0 of 4096^2: 0.77 ms against 0.85 ms per sweep,
+// although the row kernel moves 2.4 GB instead of 3.4 GB) -- the row kernel wins where the launches themselves are the cost
+template <typename T>
+__global__ void __launch_bounds__(128)
+gs25_kernel(Lev25<T> L, int colour, const int* __restrict__ done) {
+    if (done && *done) return;
+    gs25_pixel(L, colour, (int)blockIdx.y, (int)(blockIdx.x * blockDim.x + threadIdx.x));
+}
+#define GS25_COLOUR_LAUNCH_PIXELS (1LL << 22)     // levels of 2048^2 pixels and more: one launch per colour
 #define GS25_ROW_THREADS 512
 template <typename T>
 __global__ void __launch_bounds__(GS25_ROW_THREADS)

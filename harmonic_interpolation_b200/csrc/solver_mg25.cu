@@ -56,6 +56,13 @@ int Solver<T>::build_hierarchy25() {
 template <typename T>
 void Solver<T>::gs25(Lev25<T>& L, bool forward, const int* done) {
     const int c3 = (L.cols + 2) / 3;
+    if ((long long)L.rows * L.cols >= GS25_COLOUR_LAUNCH_PIXELS) {
+        dim3 gg((c3 + 127) / 128, (L.rows + 2) / 3);
+        for (int s = 0; s < mg25_sweeps; ++s)
+            for (int c = 0; c < 9; ++c) gs25_kernel<T><<<gg, 128, 0, stream>>>(L, forward ? c : 8 - c, done);
+        launches += 9 * mg25_sweeps;
+        return;
+    }
     const int threads = std::min(GS25_ROW_THREADS, round_up(c3, 32));
     for (int s = 0; s < mg25_sweeps; ++s)
         for (int q = 0; q < 3; ++q) gs25_rows_kernel<T><<<(L.rows + 2) / 3, threads, 0, stream>>>(L, forward ? q : 2 - q, forward ? 1 : 0, done);
