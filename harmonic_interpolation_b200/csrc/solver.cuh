@@ -33,6 +33,7 @@
 #include "fine_vec.cuh"
 #include "mg.cuh"
 #include "mg25.cuh"
+#include "mg25_clusters.cuh"
 #include "pcg.cuh"
 #include "stencil.cuh"
 
@@ -365,6 +366,12 @@ struct Solver : SolverBase {
 
     // ---- bilaplacian hierarchy --------------------------------------------------------------------
     int build_hierarchy25();
+    // cluster-flat transfers of level 0 for stiff gradient constraints (mg25_clusters.cuh); HGRID_MG25_CLUSTERS=0 switches them off
+    Clusters cl25 = {nullptr, nullptr, 0};
+    T *cl_sum = nullptr, *cl_tmp = nullptr;      // K fine planes each: cluster sums; the prolongated correction
+    int build_clusters25();
+    void cluster_average(T* v, int nplanes);
+    int probe_level1(const Lev25<T>& L0, Lev25<T>& L1);
     void gs25(Lev25<T>& L, bool forward, const int* done);
     // z = M^-1 r: one symmetric V-cycle from the zero guess on the 25-point hierarchy (level 0 works in place on z, r)
     int vcycle25(T* z, T* r, const int* done);

@@ -17,6 +17,8 @@ void Solver<T>::free_hierarchy() {
         if (l > 0) { dfree(lev25[l].x); dfree(lev25[l].b); }
     }
     lev25.clear();
+    dfree(cl25.label); dfree(cl25.count); dfree(cl_sum); dfree(cl_tmp);
+    cl25.label = cl25.count = nullptr; cl25.members = 0; cl_sum = cl_tmp = nullptr;
     dfree(d_dense25);
     d_dense25 = nullptr;
 }
