@@ -21,7 +21,7 @@
 namespace hg {
 
 #define CL_ROUNDS 48
-#define CL_SPACING 8
+#define CL_SPACING 6
 
 struct Clusters {
     int* label;        // per pixel: the cluster's label (the smallest pixel offset in it), -1 = not in a cluster
